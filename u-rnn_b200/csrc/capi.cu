@@ -1,0 +1,199 @@
+// capi.cu -- the extern "C" surface of liburnn_b200.so (see include/urnn_b200.h) and the whole-step driver.
+#include <atomic>
+#include <mutex>
+#include <string.h>
+
+#include "urnn_common.cuh"
+#include "urnn_internal.h"
+
+namespace urnn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int check_cell(const urnn_cell_desc* d, const urnn_cell_params* p, const float* e, const float* h,
+                      const float* h_out) {
+    URNN_CHECK_ARG(d && p, "cgru: null descriptor/params");
+    URNN_CHECK_ARG(d->H > 0 && d->W > 0, "cgru: bad grid %dx%d", d->H, d->W);
+    URNN_CHECK_ARG(d->W % 4 == 0, "cgru: W=%d must be a multiple of 4 (16-byte rows)", d->W);
+    URNN_CHECK_ARG(d->F > 0 && d->F % 32 == 0, "cgru: num_features=%d must be a multiple of 32 (GroupNorm(F//32))", d->F);
+    URNN_CHECK_ARG(d->Cx >= 0, "cgru: Cx=%d", d->Cx);
+    URNN_CHECK_ARG(d->ksize >= 1 && d->ksize % 2 == 1 && d->ksize <= 7, "cgru: filter_size=%d must be odd and <= 7", d->ksize);
+    URNN_CHECK_ARG(d->variant == URNN_CELL_ENCODER || d->variant == URNN_CELL_DECODER, "cgru: bad variant %d", d->variant);
+    URNN_CHECK_ARG((long)d->H * d->W * 2 * d->F < (1L << 31), "cgru: grid too large for 32-bit tile indexing");
+    URNN_CHECK_ARG(h && h_out, "cgru: null state pointer");
+    URNN_CHECK_ARG((d->variant == URNN_CELL_DECODER) == (e != nullptr), "cgru: e must be given exactly for the decoder variant");
+    URNN_CHECK_ARG(p->w1 && p->b1 && p->gn1_w && p->gn1_b && p->w2 && p->b2 && p->gn2_w && p->gn2_b, "cgru: null parameter");
+    return URNN_OK;
+}
+
+}  // namespace urnn
+
+using namespace urnn;
+
+extern "C" {
+
+int urnn_abi_version(void) { return URNN_ABI_VERSION; }
+const char* urnn_last_error(void) { return g_err; }
+uint64_t urnn_launch_count(void) { return g_launches.load(); }
+
+size_t urnn_cgru_fwd_workspace_bytes(const urnn_cell_desc* d) {
+    if (!d || d->F <= 0 || d->F % 32) return 0;
+    return cgru_fwd_fp32_workspace(d);
+}
+
+int urnn_cgru_fwd(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+                  const float* h, float* h_out, void* ws, size_t ws_bytes, void* stream) {
+    URNN_TRY(check_cell(d, p, e, h, h_out));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (d->math) {
+        case URNN_MATH_FP32: return cgru_fwd_fp32(d, p, x, e, h, h_out, ws, ws_bytes, st);
+        default: set_error("cgru_fwd: math mode %d not built", d->math); return URNN_E_UNSUPPORTED;
+    }
+}
+
+size_t urnn_cgru_bwd_workspace_bytes(const urnn_cell_desc*) { return 0; }
+int urnn_cgru_bwd(const urnn_cell_desc*, const urnn_cell_params*, const float*, const float*, const float*,
+                  const float*, float*, float*, float*, const urnn_cell_grads*, void*, size_t, void*) {
+    set_error("cgru_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+}
+
+int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool, float slope,
+                           const float* x, const float* w, const float* b, float* y, void* stream) {
+    URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0, "conv1x1: bad shape");
+    URNN_CHECK_ARG(pool == 1 || pool == 2, "conv1x1: pool must be 1 or 2");
+    URNN_CHECK_ARG(pool == 1 ? (W % 4 == 0) : (W % 2 == 0 && H % 2 == 0), "conv1x1: W=%d H=%d alignment", W, H);
+    URNN_CHECK_ARG(x && w && b && y, "conv1x1: null pointer");
+    return conv1x1_lrelu_fwd_fp32(Cin, Cout, H, W, pool, slope, x, w, b, y, (cudaStream_t)stream);
+}
+size_t urnn_conv1x1_lrelu_bwd_workspace_bytes(int32_t, int32_t, int32_t, int32_t, int32_t) { return 0; }
+int urnn_conv1x1_lrelu_bwd(int32_t, int32_t, int32_t, int32_t, int32_t, float, const float*, const float*,
+                           const float*, const float*, float*, float*, float*, void*, size_t, void*) {
+    set_error("conv1x1_lrelu_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+}
+
+int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope, const float* x,
+                             const float* w, const float* b, float* y, void* stream) {
+    URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0 && W % 4 == 0, "deconv2x2: bad shape (W %% 4 == 0 required)");
+    URNN_CHECK_ARG(x && w && b && y, "deconv2x2: null pointer");
+    return deconv2x2_lrelu_fwd_fp32(Cin, Cout, H, W, slope, x, w, b, y, (cudaStream_t)stream);
+}
+size_t urnn_deconv2x2_lrelu_bwd_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
+int urnn_deconv2x2_lrelu_bwd(int32_t, int32_t, int32_t, int32_t, float, const float*, const float*, const float*,
+                             const float*, float*, float*, float*, void*, size_t, void*) {
+    set_error("deconv2x2_lrelu_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+}
+
+size_t urnn_head_fwd_workspace_bytes(int32_t H, int32_t W) { return head_fwd_fp32_workspace(H, W); }
+int urnn_head_fwd(int32_t H, int32_t W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
+                  const float* feat, float* out, void* ws, size_t ws_bytes, void* stream) {
+    URNN_CHECK_ARG(H > 0 && W > 0 && p && feat && out, "head: bad argument");
+    return head_fwd_fp32(H, W, cls_thred, ln_eps, slope, p, feat, out, ws, ws_bytes, (cudaStream_t)stream);
+}
+size_t urnn_head_bwd_workspace_bytes(int32_t, int32_t) { return 0; }
+int urnn_head_bwd(int32_t, int32_t, float, float, float, const urnn_head_params*, const float*, const float*,
+                  float*, const urnn_head_grads*, void*, size_t, void*) {
+    set_error("head_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------ whole step
+struct EdPlan {
+    urnn_cell_desc enc[3], dec[3];
+    int h[3], w[3];                       // spatial size per scale (1x, 1/2, 1/4)
+    float *s[3], *up3, *up2, *feat;       // stem outputs, deconv outputs, decoder features
+    void* cell_ws; size_t cell_ws_bytes;
+    void* head_ws; size_t head_ws_bytes;
+    size_t total;
+};
+
+static int ed_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, EdPlan* pl) {
+    URNN_CHECK_ARG(d, "ed: null descriptor");
+    URNN_CHECK_ARG(d->H > 0 && d->W > 0 && d->H % 4 == 0 && d->W % 4 == 0,
+                   "ed: H=%d W=%d must be multiples of 4 (two 2x pools and two 2x deconvs must round-trip)", d->H, d->W);
+    URNN_CHECK_ARG(d->W % 16 == 0 || true, "ed: unreachable");
+    URNN_CHECK_ARG(d->ksize == 1, "ed: filter_size=%d; the encoder-decoder only works with 1x1 gates", d->ksize);
+    URNN_CHECK_ARG(d->dec_conv[2] == 16, "ed: decoder.conv_out_channels[-1]=%d must be 16 (head width, model.py:62-63)", d->dec_conv[2]);
+    URNN_CHECK_ARG(d->Cin > 0, "ed: Cin=%d", d->Cin);
+    URNN_CHECK_ARG(d->dec_gru[0] == d->enc_gru[2] && d->dec_gru[1] == d->enc_gru[1] && d->dec_gru[2] == d->enc_gru[0],
+                   "ed: decoder gru_channels must mirror the encoder's (skip concat, decoder.py:135)");
+    URNN_CHECK_ARG((d->W / 4) % 4 == 0, "ed: W=%d must be a multiple of 16 (16-byte rows at quarter resolution)", d->W);
+    for (int k = 0; k < 3; ++k) { pl->h[k] = d->H >> k; pl->w[k] = d->W >> k; }
+    for (int k = 0; k < 3; ++k) {
+        pl->enc[k] = urnn_cell_desc{pl->h[k], pl->w[k], d->enc_conv[k], d->enc_gru[k], 1, URNN_CELL_ENCODER, d->math, d->gn_eps};
+        int sc = 2 - k;                   // decoder index 0 is the deepest scale
+        int cx = (k == 0) ? d->dec_conv[0] : d->dec_conv[k - 1];
+        pl->dec[k] = urnn_cell_desc{pl->h[sc], pl->w[sc], cx, d->dec_gru[k], 1, URNN_CELL_DECODER, d->math, d->gn_eps};
+    }
+    Arena a(ws, ws_bytes);
+    for (int k = 0; k < 3; ++k) pl->s[k] = a.take<float>((size_t)d->enc_conv[k] * pl->h[k] * pl->w[k]);
+    pl->up3 = a.take<float>((size_t)d->dec_conv[0] * pl->h[1] * pl->w[1]);
+    pl->up2 = a.take<float>((size_t)d->dec_conv[1] * pl->h[0] * pl->w[0]);
+    pl->feat = a.take<float>((size_t)16 * d->H * d->W);
+    size_t cw = 0;
+    for (int k = 0; k < 3; ++k) {
+        size_t a1 = urnn_cgru_fwd_workspace_bytes(&pl->enc[k]), a2 = urnn_cgru_fwd_workspace_bytes(&pl->dec[k]);
+        URNN_CHECK_ARG(a1 && a2, "ed: gru_channels must be multiples of 32");
+        cw = a1 > cw ? a1 : cw; cw = a2 > cw ? a2 : cw;
+    }
+    pl->cell_ws_bytes = cw;
+    pl->cell_ws = a.take<char>(cw);
+    pl->head_ws_bytes = urnn_head_fwd_workspace_bytes(d->H, d->W);
+    pl->head_ws = a.take<char>(pl->head_ws_bytes);
+    pl->total = align_up(a.off, 256);
+    return URNN_OK;
+}
+
+size_t urnn_ed_step_workspace_bytes(const urnn_ed_desc* d) {
+    EdPlan pl;
+    if (ed_plan(d, nullptr, 0, &pl) != URNN_OK) return 0;
+    return pl.total;
+}
+
+int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float* input,
+                     const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes,
+                     void* stream) {
+    EdPlan pl;
+    URNN_TRY(ed_plan(d, ws, ws_bytes, &pl));
+    URNN_CHECK_ARG(p && input && sin && sout && out, "ed_step: null pointer");
+    if (pl.total > ws_bytes) { set_error("ed_step: workspace %zu < %zu bytes", ws_bytes, pl.total); return URNN_E_WORKSPACE; }
+    for (int i = 0; i < 6; ++i) URNN_CHECK_ARG(sin[i] && sout[i] && sin[i] != sout[i], "ed_step: state %d null or aliased", i);
+    const float sl = d->lrelu_slope;
+    // ---- encoder (encoder.py:187-215): stem conv (+pool) then ConvGRU, stage k feeds stage k+1
+    const float* cur = input; int cin = d->Cin;
+    for (int k = 0; k < 3; ++k) {
+        int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
+        URNN_TRY(urnn_conv1x1_lrelu_fwd(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, p->enc_stem_w[k],
+                                        p->enc_stem_b[k], pl.s[k], stream));
+        URNN_TRY(urnn_cgru_fwd(&pl.enc[k], &p->enc_cell[k], pl.s[k], nullptr, sin[k], sout[k], pl.cell_ws,
+                               pl.cell_ws_bytes, stream));
+        cur = sout[k]; cin = d->enc_gru[k];
+    }
+    // ---- decoder (decoder.py:173-217): deepest first; x of the deepest stage is None -> zeros
+    URNN_TRY(urnn_cgru_fwd(&pl.dec[0], &p->dec_cell[0], nullptr, sout[2], sin[3], sout[3], pl.cell_ws, pl.cell_ws_bytes, stream));
+    URNN_TRY(urnn_deconv2x2_lrelu_fwd(d->dec_gru[0], d->dec_conv[0], pl.h[2], pl.w[2], sl, sout[3], p->dec_stem_w[0],
+                                      p->dec_stem_b[0], pl.up3, stream));
+    URNN_TRY(urnn_cgru_fwd(&pl.dec[1], &p->dec_cell[1], pl.up3, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, stream));
+    URNN_TRY(urnn_deconv2x2_lrelu_fwd(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, sout[4], p->dec_stem_w[1],
+                                      p->dec_stem_b[1], pl.up2, stream));
+    URNN_TRY(urnn_cgru_fwd(&pl.dec[2], &p->dec_cell[2], pl.up2, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, stream));
+    URNN_TRY(urnn_conv1x1_lrelu_fwd(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], p->dec_stem_w[2], p->dec_stem_b[2],
+                                    pl.feat, stream));
+    // ---- head (flood_head.py:131-177)
+    URNN_TRY(urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream));
+    return URNN_OK;
+}
+
+size_t urnn_ed_sequence_host_workspace_bytes(const urnn_ed_desc*) { return 0; }
+int urnn_ed_sequence_host(const urnn_ed_desc*, const urnn_ed_params*, int32_t, const float*, float*, float* const*,
+                          void*, size_t, void*) {
+    set_error("ed_sequence_host: not implemented in this build"); return URNN_E_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+// pixgemm.cuh -- fp32 "pixel GEMM": out[M x pixels] = A[M x K] * B[K x pixels] with pluggable B-tile loaders
+// (virtual channel concatenation, gating, pooling gather, k x k taps) and fused epilogues.
+// This is the URNN_MATH_FP32 parity path (FFMA, fp32 accumulate); the tcgen05 path lives in cgru_tc.cu.
+//
+// Tiling: CTA = 256 threads = 8 (channel dim, ty) x 32 (pixel dim, tx); CTA tile = (8*TM) outputs x 128 pixels;
+// thread tile = TM outputs x 4 consecutive pixels; K is consumed in slabs of 16 through double-buffered
+// shared memory with register prefetch.  For TM % 4 == 0 a thread's outputs are 4 consecutive channels in each
+// 32-channel block (ch = (i/4)*32 + ty*4 + i%4) so that one GroupNorm group (32 channels) is spread over the
+// whole CTA and group statistics fall out of a CTA-wide reduction.
+#pragma once
+#include "urnn_common.cuh"
+
+namespace urnn {
+
+constexpr int PG_BN = 128;   // pixels per CTA tile
+constexpr int PG_BK = 16;    // K slab
+
+template <int TM>
+__device__ __forceinline__ int pg_channel(int ty, int i) {
+    if constexpr (TM % 4 == 0) return (i >> 2) * 32 + ty * 4 + (i & 3);
+    else return ty * TM + i;
+}
+
+// A operand addressing: A(m,k) = A[m*sm + k*sk]
+struct AView { const float* ptr; long sm; long sk; };
+
+template <int TM, class BLoader, class Epilogue>
+__global__ void __launch_bounds__(256)
+pixgemm_kernel(AView A, int M, int K, int N, BLoader bl, Epilogue epi) {
+    constexpr int BM = TM * 8;
+    constexpr int AS = BM + 4;                       // padded row (keeps 16B alignment)
+    constexpr int AR = (BM * PG_BK + 255) / 256;     // A elements per thread per slab
+    __shared__ __align__(16) float As[2][PG_BK][AS];
+    __shared__ __align__(16) float Bs[2][PG_BK][PG_BN];
+
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int p0 = blockIdx.x * PG_BN;
+    const int m0 = blockIdx.y * BM;
+
+    bl.init(p0, N);   // per-CTA loader setup (may use shared memory + __syncthreads)
+
+    float acc[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+    float4 breg[2];
+    float  areg[AR];
+    const int nk = (K + PG_BK - 1) / PG_BK;
+    const bool a_kcontig = (A.sk == 1);
+
+    auto gload = [&](int kt) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int idx = tid + i * 256;
+            int kk = idx >> 5, q = idx & 31;
+            int k = kt * PG_BK + kk;
+            breg[i] = (k < K) ? bl.load4(k, p0 + q * 4, N) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < AR; ++i) {
+            int idx = tid + i * 256;
+            float v = 0.f;
+            if (idx < BM * PG_BK) {
+                int m, kk;
+                if (a_kcontig) { m = idx / PG_BK; kk = idx % PG_BK; }
+                else           { kk = idx / BM;   m = idx % BM; }
+                int k = kt * PG_BK + kk;
+                if (k < K && m0 + m < M) v = __ldg(A.ptr + (long)(m0 + m) * A.sm + (long)k * A.sk);
+            }
+            areg[i] = v;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int idx = tid + i * 256;
+            int kk = idx >> 5, q = idx & 31;
+            *reinterpret_cast<float4*>(&Bs[buf][kk][q * 4]) = breg[i];
+        }
+#pragma unroll
+        for (int i = 0; i < AR; ++i) {
+            int idx = tid + i * 256;
+            if (idx < BM * PG_BK) {
+                int m, kk;
+                if (a_kcontig) { m = idx / PG_BK; kk = idx % PG_BK; }
+                else           { kk = idx / BM;   m = idx % BM; }
+                As[buf][kk][m] = areg[i];
+            }
+        }
+    };
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int cur = kt & 1;
+        if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+        for (int kk = 0; kk < PG_BK; ++kk) {
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+            if constexpr (TM % 4 == 0) {
+#pragma unroll
+                for (int j = 0; j < TM / 4; ++j) {
+                    const float4 a = *reinterpret_cast<const float4*>(&As[cur][kk][j * 32 + ty * 4]);
+                    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[j * 4 + u][0] = fmaf(av[u], b.x, acc[j * 4 + u][0]);
+                        acc[j * 4 + u][1] = fmaf(av[u], b.y, acc[j * 4 + u][1]);
+                        acc[j * 4 + u][2] = fmaf(av[u], b.z, acc[j * 4 + u][2]);
+                        acc[j * 4 + u][3] = fmaf(av[u], b.w, acc[j * 4 + u][3]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    const float a = As[cur][kk][ty * TM + i];
+                    acc[i][0] = fmaf(a, b.x, acc[i][0]);
+                    acc[i][1] = fmaf(a, b.y, acc[i][1]);
+                    acc[i][2] = fmaf(a, b.z, acc[i][2]);
+                    acc[i][3] = fmaf(a, b.w, acc[i][3]);
+                }
+            }
+        }
+        if (kt + 1 < nk) {
+            sstore(cur ^ 1);
+            __syncthreads();
+        }
+    }
+    epi.template run<TM>(acc, m0, M, ty, tx, p0 + tx * 4, N);
+}
+
+// ------------------------------------------------------------------------------------------------ B loaders
+// load4(k, p, N): the 4 values of reduction row k at tile units p..p+3 (p % 4 == 0), zeros past N.
+
+// k = 1: channel concatenation of up to three NCHW sources; optional reset gate on the last segment:
+// value = src * sigmoid(G[gch0 + c] * scale[gch0 + c] + shift[gch0 + c]).
+struct SegLoader {
+    const float* src[3]; int cnt[3];        // cumulative ends in cend
+    int cend[3];
+    long plane;                             // elements per channel plane (= N)
+    const float* gate_pre; const float* gate_scale; const float* gate_shift; int gate_ch0;  // nullptr => no gate
+    __device__ __forceinline__ void init(int, int) {}
+    __device__ __forceinline__ float4 load4(int k, int p, int N) const {
+        if (p >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
+        int seg = (k < cend[0]) ? 0 : ((k < cend[1]) ? 1 : 2);
+        int c = k - (seg == 0 ? 0 : cend[seg - 1]);
+        float4 v = __ldg(reinterpret_cast<const float4*>(src[seg] + (long)c * plane + p));
+        bool last = (seg == 2) || (seg == 1 && cnt[2] == 0);
+        if (gate_pre != nullptr && last) {
+            int gc = gate_ch0 + c;
+            float4 g = __ldg(reinterpret_cast<const float4*>(gate_pre + (long)gc * plane + p));
+            float sc = __ldg(gate_scale + gc), sh = __ldg(gate_shift + gc);
+            v.x *= sigmoid_acc(fmaf(g.x, sc, sh));
+            v.y *= sigmoid_acc(fmaf(g.y, sc, sh));
+            v.z *= sigmoid_acc(fmaf(g.z, sc, sh));
+            v.w *= sigmoid_acc(fmaf(g.w, sc, sh));
+        }
+        return v;
+    }
+};
+
+// k x k taps (odd k, zero padding (k-1)/2): reduction index = (c_concat * k + dy) * k + dx, matching the
+// nn.Conv2d weight layout (Cout, Cin, k, k).  Same segment/gate semantics as SegLoader.
+struct TapLoader {
+    const float* src[3]; int cnt[3]; int cend[3];
+    long plane; int H, W, ks;
+    const float* gate_pre; const float* gate_scale; const float* gate_shift; int gate_ch0;
+    __device__ __forceinline__ void init(int, int) {}
+    __device__ __forceinline__ float4 load4(int k, int p, int N) const {
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
+        int kk = ks * ks;
+        int cc = k / kk, tap = k % kk, dy = tap / ks - (ks - 1) / 2, dx = tap % ks - (ks - 1) / 2;
+        int seg = (cc < cend[0]) ? 0 : ((cc < cend[1]) ? 1 : 2);
+        int c = cc - (seg == 0 ? 0 : cend[seg - 1]);
+        bool last = (seg == 2) || (seg == 1 && cnt[2] == 0);
+        bool gated = gate_pre != nullptr && last;
+        int y = p / W, x0 = p % W;          // W % 4 == 0 so the 4 pixels share a row
+        int yy = y + dy;
+        if (yy < 0 || yy >= H) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* base = src[seg] + (long)c * plane + (long)yy * W;
+        float sc = 0.f, sh = 0.f; const float* gbase = nullptr;
+        if (gated) {
+            int gc = gate_ch0 + c;
+            sc = __ldg(gate_scale + gc); sh = __ldg(gate_shift + gc);
+            gbase = gate_pre + (long)gc * plane + (long)yy * W;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int xx = x0 + u + dx;
+            if (xx >= 0 && xx < W) {
+                float v = __ldg(base + xx);
+                if (gated) v *= sigmoid_acc(fmaf(__ldg(gbase + xx), sc, sh));
+                out[u] = v;
+            }
+        }
+        return make_float4(out[0], out[1], out[2], out[3]);
+    }
+};
+
+// 2x2 pooling gather: tile unit q = 4*Q + s addresses sub-pixel s of the 2x2 quad Q of a (C,H,W) source,
+// so that a thread's 4 "pixels" are exactly one pooling window.  N = 4 * (H/2) * (W/2).
+struct QuadLoader {
+    const float* src; long plane; int W, W2;
+    __device__ __forceinline__ void init(int, int) {}
+    __device__ __forceinline__ float4 load4(int k, int p, int N) const {
+        if (p >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
+        int Q = p >> 2;
+        int qy = Q / W2, qx = Q % W2;
+        const float* b = src + (long)k * plane + (long)(2 * qy) * W + 2 * qx;
+        float2 t = __ldg(reinterpret_cast<const float2*>(b));
+        float2 u = __ldg(reinterpret_cast<const float2*>(b + W));
+        return make_float4(t.x, t.y, u.x, u.y);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ epilogues
+// out[ch][pixel] = acc + bias[ch]; per-32-channel-group (sum, sumsq) partials -> StatSink (GroupNorm).
+struct GnStatsEpilogue {
+    static constexpr bool kAllowSmallTM = false;
+    const float* bias; float* out; long plane;
+    StatSink sink; AffineOut aff;
+    template <int TM>
+    __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
+        static_assert(TM % 4 == 0, "GroupNorm epilogue needs 32-channel blocks");
+        constexpr int NG = TM / 4;
+        __shared__ float red[2][NG][8];
+        const bool valid = p < N;
+        float s[NG], ss[NG];
+#pragma unroll
+        for (int j = 0; j < NG; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int ch = m0 + pg_channel<TM>(ty, i);
+            float b = __ldg(bias + ch);
+            float4 v = make_float4(acc[i][0] + b, acc[i][1] + b, acc[i][2] + b, acc[i][3] + b);
+            if (valid) {
+                *reinterpret_cast<float4*>(out + (long)ch * plane + p) = v;
+                s[i >> 2] += (v.x + v.y) + (v.z + v.w);
+                ss[i >> 2] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            float a = warp_sum(s[j]), b = warp_sum(ss[j]);
+            if (tx == 0) { red[0][j][ty] = a; red[1][j][ty] = b; }
+        }
+        __syncthreads();
+        if (threadIdx.x < NG) {
+            int j = threadIdx.x;
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { a += red[0][j][w]; b += red[1][j][w]; }
+            int set = blockIdx.y * NG + j;
+            sink.partial[(size_t)set * sink.stride + blockIdx.x] = make_float2(a, b);
+        }
+        stats_finalize_last_cta(sink, gridDim.x, gridDim.x * gridDim.y, &aff);
+    }
+};
+
+// y = lrelu(acc + bias), stored NCHW.
+struct LreluEpilogue {
+    static constexpr bool kAllowSmallTM = true;
+    const float* bias; float* out; long plane; float slope;
+    template <int TM>
+    __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
+        if (p >= N) return;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int ch = m0 + pg_channel<TM>(ty, i);
+            if (ch >= M) continue;
+            float b = __ldg(bias + ch);
+            float4 v = make_float4(lrelu(acc[i][0] + b, slope), lrelu(acc[i][1] + b, slope),
+                                   lrelu(acc[i][2] + b, slope), lrelu(acc[i][3] + b, slope));
+            *reinterpret_cast<float4*>(out + (long)ch * plane + p) = v;
+        }
+    }
+};
+
+// y[ch][Q] = mean over the quad of lrelu(acc + bias)   (used with QuadLoader; plane = (H/2)*(W/2)).
+struct LreluPoolEpilogue {
+    static constexpr bool kAllowSmallTM = true;
+    const float* bias; float* out; long plane; float slope;
+    template <int TM>
+    __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
+        if (p >= N) return;
+        int Q = p >> 2;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int ch = m0 + pg_channel<TM>(ty, i);
+            if (ch >= M) continue;
+            float b = __ldg(bias + ch);
+            float v = (lrelu(acc[i][0] + b, slope) + lrelu(acc[i][1] + b, slope)) +
+                      (lrelu(acc[i][2] + b, slope) + lrelu(acc[i][3] + b, slope));
+            out[(long)ch * plane + Q] = 0.25f * v;
+        }
+    }
+};
+
+// ConvTranspose2d(k=2,s=2) scatter: GEMM row m = co*4 + dy*2 + dx; y[co][2y+dy][2x+dx] = lrelu(acc + bias[co]).
+struct DeconvEpilogue {
+    static constexpr bool kAllowSmallTM = false;
+    const float* bias; float* out; int W; float slope;   // W = input width; output plane = 4*H*W
+    long oplane;
+    template <int TM>
+    __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
+        static_assert(TM % 4 == 0, "deconv epilogue needs 4 consecutive rows per thread");
+        if (p >= N) return;
+        int y = p / W, x0 = p % W;
+#pragma unroll
+        for (int j = 0; j < TM / 4; ++j) {
+            int m = m0 + pg_channel<TM>(ty, j * 4);
+            if (m >= M) continue;
+            int co = m >> 2;
+            float b = __ldg(bias + co);
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                float* o = out + (long)co * oplane + (long)(2 * y + dy) * (2 * W) + 2 * x0;
+                const float* e = acc[j * 4 + dy * 2];       // dx = 0
+                const float* f = acc[j * 4 + dy * 2 + 1];   // dx = 1
+                float4 v0 = make_float4(lrelu(e[0] + b, slope), lrelu(f[0] + b, slope),
+                                        lrelu(e[1] + b, slope), lrelu(f[1] + b, slope));
+                float4 v1 = make_float4(lrelu(e[2] + b, slope), lrelu(f[2] + b, slope),
+                                        lrelu(e[3] + b, slope), lrelu(f[3] + b, slope));
+                *reinterpret_cast<float4*>(o) = v0;
+                *reinterpret_cast<float4*>(o + 4) = v1;
+            }
+        }
+    }
+};
+
+}  // namespace urnn

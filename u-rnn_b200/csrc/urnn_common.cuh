@@ -1,0 +1,130 @@
+// urnn_common.cuh -- shared helpers for liburnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/urnn_b200.h"
+
+namespace urnn {
+
+// ---- error reporting (thread-local message, C-ABI return codes) -------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define URNN_CHECK_ARG(cond, ...)                                  \
+    do { if (!(cond)) { ::urnn::set_error(__VA_ARGS__); return URNN_E_INVALID; } } while (0)
+
+#define URNN_CUDA(call)                                                                     \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                                  \
+        ::urnn::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        return URNN_E_CUDA; } } while (0)
+
+#define URNN_LAUNCH_CHECK()                                                                 \
+    do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) {                      \
+        ::urnn::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+        return URNN_E_CUDA; } ::urnn::count_launch(); } while (0)
+
+#define URNN_TRY(call) do { int r_ = (call); if (r_ != URNN_OK) return r_; } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+    char* base; size_t size; size_t off;
+    Arena(void* p, size_t n) : base((char*)p), size(n), off(0) {}
+    template <class T> T* take(size_t count) {
+        off = align_up(off, 256);
+        T* r = (T*)(base + off);
+        off += count * sizeof(T);
+        return r;
+    }
+    bool ok() const { return off <= size; }
+};
+
+// ---- device math -------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float lrelu(float x, float slope) { return x >= 0.f ? x : x * slope; }
+__device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- normalisation statistics ------------------------------------------------------------------
+// A "stat set" is one normalisation group: (sum, sum of squares) over its elements.  Producers write one
+// float2 partial per CTA into partial[set * stride + cta]; the last CTA to finish (ticket counter) sums the
+// partials of every set in a fixed order in double and writes total[set]; the result is therefore
+// run-to-run deterministic.  The counter resets itself so the same control block can be reused.
+struct StatSink {
+    float2*   partial;   // [nsets][stride]
+    double2*  total;     // [nsets]
+    unsigned* counter;   // one ticket counter for this launch
+    int       nsets;
+    int       stride;    // >= number of CTAs contributing to a set
+};
+
+// Called by ALL threads of the CTA after the CTA's partials are written and made visible.
+// ncontrib = CTAs contributing per set, ncta_total = CTAs in the launch.  Optionally the last CTA also
+// folds the totals into per-channel affine (scale, shift) so consumers apply y = x*scale + shift:
+//   scale[c] = gamma[c]*rstd[g(c)],  shift[c] = beta[c] - mean[g(c)]*scale[c],  g(c) = c / ch_per_set.
+struct AffineOut {
+    float* scale; float* shift; const float* gamma; const float* beta;
+    int channels; int ch_per_set; double count; float eps;
+};
+
+__device__ __forceinline__ void stats_finalize_last_cta(const StatSink& s, int ncontrib, unsigned ncta_total,
+                                                        const AffineOut* aff) {
+    __shared__ bool is_last;
+    __shared__ double red[2][8];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(s.counter, 1u);
+        is_last = (t == ncta_total - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int nwarp = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int set = 0; set < s.nsets; ++set) {
+        double a = 0.0, b = 0.0;
+        for (int i = threadIdx.x; i < ncontrib; i += blockDim.x) {
+            float2 v = __ldcg(&s.partial[(size_t)set * s.stride + i]);
+            a += (double)v.x; b += (double)v.y;
+        }
+        a = warp_sum(a); b = warp_sum(b);
+        if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ta = 0.0, tb = 0.0;
+            for (int w = 0; w < nwarp; ++w) { ta += red[0][w]; tb += red[1][w]; }
+            s.total[set] = make_double2(ta, tb);
+        }
+        __syncthreads();
+    }
+    if (aff != nullptr) {
+        __threadfence();
+        for (int c = threadIdx.x; c < aff->channels; c += blockDim.x) {
+            double2 t = s.total[c / aff->ch_per_set];
+            double mean = t.x / aff->count;
+            double var = t.y / aff->count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            double rstd = 1.0 / sqrt(var + (double)aff->eps);
+            double sc = (double)aff->gamma[c] * rstd;
+            aff->scale[c] = (float)sc;
+            aff->shift[c] = (float)((double)aff->beta[c] - mean * sc);
+        }
+    }
+    if (threadIdx.x == 0) *s.counter = 0u;
+}
+
+}  // namespace urnn

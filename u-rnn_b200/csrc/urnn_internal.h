@@ -1,0 +1,20 @@
+// urnn_internal.h -- internal (C++) interfaces between the translation units of liburnn_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/urnn_b200.h"
+
+namespace urnn {
+
+// fp32 FFMA path (urnn_fp32.cu)
+size_t cgru_fwd_fp32_workspace(const urnn_cell_desc* d);
+int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int conv1x1_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, int pool, float slope, const float* x,
+                           const float* w, const float* b, float* y, cudaStream_t st);
+int deconv2x2_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, float slope, const float* x, const float* w,
+                             const float* b, float* y, cudaStream_t st);
+size_t head_fwd_fp32_workspace(int H, int W);
+int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
+                  const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace urnn
