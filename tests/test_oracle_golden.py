@@ -79,3 +79,21 @@ def test_synthetic_inputs_shape():
     xs = O.synthetic_event_inputs(8, 12, 5, 3)
     assert xs.shape == (5, 9, 8, 12) and xs.dtype == np.float32
     assert np.all(xs[0, :2] == 0) and np.all(xs[0, 3:5] == 0)     # zero-padded history at t=0
+
+
+def test_torch_port_matches_reference(golden_dir):
+    """The functional-torch port (bench.py's CPU baseline) reproduces the reference's outputs."""
+    from oracle import torch_port as TP
+    z, w = load(golden_dir, "ed_32x32_c9")
+    p = {k: torch.from_numpy(v.astype(np.float32)) for k, v in w.items()}
+    H, W, hist, T, _ = [int(v) for v in z["meta"]]
+    xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, hist))
+    st = [torch.from_numpy(s)[None] for s in O.zero_states(H, W)]
+    with torch.no_grad():
+        for t in range(T):
+            depth, prob, st = TP.ed_step(p, xs[t][None], st)
+            np.testing.assert_allclose(prob.numpy()[0, 0], z["prob"][t], atol=ATOL, rtol=RTOL)
+            safe = np.abs(z["prob"][t] - 0.5) > 1e-5
+            np.testing.assert_allclose(depth.numpy()[0, 0][safe], z["out"][t][safe], atol=ATOL, rtol=RTOL)
+    for i in range(6):
+        np.testing.assert_allclose(st[i].numpy()[0], z[f"state{i}"], atol=ATOL, rtol=RTOL)

@@ -22,13 +22,13 @@ static int check_cell(const urnn_cell_desc* d, const urnn_cell_params* p, const 
                       const float* h_out) {
     URNN_CHECK_ARG(d && p, "cgru: null descriptor/params");
     URNN_CHECK_ARG(d->H > 0 && d->W > 0, "cgru: bad grid %dx%d", d->H, d->W);
-    URNN_CHECK_ARG(d->W % 4 == 0, "cgru: W=%d must be a multiple of 4 (16-byte rows)", d->W);
     URNN_CHECK_ARG(d->F > 0 && d->F % 32 == 0, "cgru: num_features=%d must be a multiple of 32 (GroupNorm(F//32))", d->F);
     URNN_CHECK_ARG(d->Cx >= 0, "cgru: Cx=%d", d->Cx);
     URNN_CHECK_ARG(d->ksize >= 1 && d->ksize % 2 == 1 && d->ksize <= 7, "cgru: filter_size=%d must be odd and <= 7", d->ksize);
     URNN_CHECK_ARG(d->variant == URNN_CELL_ENCODER || d->variant == URNN_CELL_DECODER, "cgru: bad variant %d", d->variant);
     URNN_CHECK_ARG((long)d->H * d->W * 2 * d->F < (1L << 31), "cgru: grid too large for 32-bit tile indexing");
     URNN_CHECK_ARG(h && h_out, "cgru: null state pointer");
+    URNN_CHECK_ARG(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0, "cgru: h and h_out must be 16-byte aligned");
     URNN_CHECK_ARG((d->variant == URNN_CELL_DECODER) == (e != nullptr), "cgru: e must be given exactly for the decoder variant");
     URNN_CHECK_ARG(p->w1 && p->b1 && p->gn1_w && p->gn1_b && p->w2 && p->b2 && p->gn2_w && p->gn2_b, "cgru: null parameter");
     return URNN_OK;
@@ -69,7 +69,8 @@ int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int3
                            const float* x, const float* w, const float* b, float* y, void* stream) {
     URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0, "conv1x1: bad shape");
     URNN_CHECK_ARG(pool == 1 || pool == 2, "conv1x1: pool must be 1 or 2");
-    URNN_CHECK_ARG(pool == 1 ? (W % 4 == 0) : (W % 2 == 0 && H % 2 == 0), "conv1x1: W=%d H=%d alignment", W, H);
+    URNN_CHECK_ARG(pool == 1 || (W % 2 == 0 && H % 2 == 0), "conv1x1: AvgPool2 needs even H=%d, W=%d", H, W);
+    URNN_CHECK_ARG(pool == 1 || (reinterpret_cast<uintptr_t>(x) & 7) == 0, "conv1x1: pooled input must be 8-byte aligned");
     URNN_CHECK_ARG(x && w && b && y, "conv1x1: null pointer");
     return conv1x1_lrelu_fwd_fp32(Cin, Cout, H, W, pool, slope, x, w, b, y, (cudaStream_t)stream);
 }
@@ -81,7 +82,8 @@ int urnn_conv1x1_lrelu_bwd(int32_t, int32_t, int32_t, int32_t, int32_t, float, c
 
 int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope, const float* x,
                              const float* w, const float* b, float* y, void* stream) {
-    URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0 && W % 4 == 0, "deconv2x2: bad shape (W %% 4 == 0 required)");
+    URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0, "deconv2x2: bad shape");
+    URNN_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 7) == 0, "deconv2x2: output must be 8-byte aligned");
     URNN_CHECK_ARG(x && w && b && y, "deconv2x2: null pointer");
     return deconv2x2_lrelu_fwd_fp32(Cin, Cout, H, W, slope, x, w, b, y, (cudaStream_t)stream);
 }
@@ -117,13 +119,11 @@ static int ed_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, EdPlan* pl)
     URNN_CHECK_ARG(d, "ed: null descriptor");
     URNN_CHECK_ARG(d->H > 0 && d->W > 0 && d->H % 4 == 0 && d->W % 4 == 0,
                    "ed: H=%d W=%d must be multiples of 4 (two 2x pools and two 2x deconvs must round-trip)", d->H, d->W);
-    URNN_CHECK_ARG(d->W % 16 == 0 || true, "ed: unreachable");
     URNN_CHECK_ARG(d->ksize == 1, "ed: filter_size=%d; the encoder-decoder only works with 1x1 gates", d->ksize);
     URNN_CHECK_ARG(d->dec_conv[2] == 16, "ed: decoder.conv_out_channels[-1]=%d must be 16 (head width, model.py:62-63)", d->dec_conv[2]);
     URNN_CHECK_ARG(d->Cin > 0, "ed: Cin=%d", d->Cin);
     URNN_CHECK_ARG(d->dec_gru[0] == d->enc_gru[2] && d->dec_gru[1] == d->enc_gru[1] && d->dec_gru[2] == d->enc_gru[0],
                    "ed: decoder gru_channels must mirror the encoder's (skip concat, decoder.py:135)");
-    URNN_CHECK_ARG((d->W / 4) % 4 == 0, "ed: W=%d must be a multiple of 16 (16-byte rows at quarter resolution)", d->W);
     for (int k = 0; k < 3; ++k) { pl->h[k] = d->H >> k; pl->w[k] = d->W >> k; }
     for (int k = 0; k < 3; ++k) {
         pl->enc[k] = urnn_cell_desc{pl->h[k], pl->w[k], d->enc_conv[k], d->enc_gru[k], 1, URNN_CELL_ENCODER, d->math, d->gn_eps};

@@ -140,16 +140,35 @@ struct SegLoader {
     int cend[3];
     long plane;                             // elements per channel plane (= N)
     const float* gate_pre; const float* gate_scale; const float* gate_shift; int gate_ch0;  // nullptr => no gate
+    bool vec;                               // plane % 4 == 0 and all bases 16-byte aligned: float4 path
     __device__ __forceinline__ void init(int, int) {}
     __device__ __forceinline__ float4 load4(int k, int p, int N) const {
         if (p >= N) return make_float4(0.f, 0.f, 0.f, 0.f);
         int seg = (k < cend[0]) ? 0 : ((k < cend[1]) ? 1 : 2);
         int c = k - (seg == 0 ? 0 : cend[seg - 1]);
-        float4 v = __ldg(reinterpret_cast<const float4*>(src[seg] + (long)c * plane + p));
+        const float* sp = src[seg] + (long)c * plane + p;
+        float4 v;
+        if (vec) {
+            v = __ldg(reinterpret_cast<const float4*>(sp));
+        } else {
+            v.x = __ldg(sp);
+            v.y = (p + 1 < N) ? __ldg(sp + 1) : 0.f;
+            v.z = (p + 2 < N) ? __ldg(sp + 2) : 0.f;
+            v.w = (p + 3 < N) ? __ldg(sp + 3) : 0.f;
+        }
         bool last = (seg == 2) || (seg == 1 && cnt[2] == 0);
         if (gate_pre != nullptr && last) {
             int gc = gate_ch0 + c;
-            float4 g = __ldg(reinterpret_cast<const float4*>(gate_pre + (long)gc * plane + p));
+            const float* gp = gate_pre + (long)gc * plane + p;
+            float4 g;
+            if (vec) {
+                g = __ldg(reinterpret_cast<const float4*>(gp));
+            } else {
+                g.x = __ldg(gp);
+                g.y = (p + 1 < N) ? __ldg(gp + 1) : 0.f;
+                g.z = (p + 2 < N) ? __ldg(gp + 2) : 0.f;
+                g.w = (p + 3 < N) ? __ldg(gp + 3) : 0.f;
+            }
             float sc = __ldg(gate_scale + gc), sh = __ldg(gate_shift + gc);
             v.x *= sigmoid_acc(fmaf(g.x, sc, sh));
             v.y *= sigmoid_acc(fmaf(g.y, sc, sh));
@@ -166,6 +185,7 @@ struct TapLoader {
     const float* src[3]; int cnt[3]; int cend[3];
     long plane; int H, W, ks;
     const float* gate_pre; const float* gate_scale; const float* gate_shift; int gate_ch0;
+    bool vec;   // unused (taps are gathered element-wise)
     __device__ __forceinline__ void init(int, int) {}
     __device__ __forceinline__ float4 load4(int k, int p, int N) const {
         float out[4] = {0.f, 0.f, 0.f, 0.f};
@@ -176,22 +196,22 @@ struct TapLoader {
         int c = cc - (seg == 0 ? 0 : cend[seg - 1]);
         bool last = (seg == 2) || (seg == 1 && cnt[2] == 0);
         bool gated = gate_pre != nullptr && last;
-        int y = p / W, x0 = p % W;          // W % 4 == 0 so the 4 pixels share a row
-        int yy = y + dy;
-        if (yy < 0 || yy >= H) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* base = src[seg] + (long)c * plane + (long)yy * W;
+        const float* base = src[seg] + (long)c * plane;
         float sc = 0.f, sh = 0.f; const float* gbase = nullptr;
         if (gated) {
             int gc = gate_ch0 + c;
             sc = __ldg(gate_scale + gc); sh = __ldg(gate_shift + gc);
-            gbase = gate_pre + (long)gc * plane + (long)yy * W;
+            gbase = gate_pre + (long)gc * plane;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            int xx = x0 + u + dx;
-            if (xx >= 0 && xx < W) {
-                float v = __ldg(base + xx);
-                if (gated) v *= sigmoid_acc(fmaf(__ldg(gbase + xx), sc, sh));
+            int q = p + u;
+            if (q >= N) break;
+            int yy = q / W + dy, xx = q % W + dx;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                long o = (long)yy * W + xx;
+                float v = __ldg(base + o);
+                if (gated) v *= sigmoid_acc(fmaf(__ldg(gbase + o), sc, sh));
                 out[u] = v;
             }
         }
@@ -219,27 +239,31 @@ struct QuadLoader {
 // out[ch][pixel] = acc + bias[ch]; per-32-channel-group (sum, sumsq) partials -> StatSink (GroupNorm).
 struct GnStatsEpilogue {
     static constexpr bool kAllowSmallTM = false;
-    const float* bias; float* out; long plane;
+    const float* bias; float* out; long plane; bool vec;
     StatSink sink; AffineOut aff;
     template <int TM>
     __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
         static_assert(TM % 4 == 0, "GroupNorm epilogue needs 32-channel blocks");
         constexpr int NG = TM / 4;
         __shared__ float red[2][NG][8];
-        const bool valid = p < N;
         float s[NG], ss[NG];
 #pragma unroll
         for (int j = 0; j < NG; ++j) { s[j] = 0.f; ss[j] = 0.f; }
+        const int nvalid = (p >= N) ? 0 : ((N - p >= 4) ? 4 : (N - p));
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
             int ch = m0 + pg_channel<TM>(ty, i);
             float b = __ldg(bias + ch);
-            float4 v = make_float4(acc[i][0] + b, acc[i][1] + b, acc[i][2] + b, acc[i][3] + b);
-            if (valid) {
-                *reinterpret_cast<float4*>(out + (long)ch * plane + p) = v;
-                s[i >> 2] += (v.x + v.y) + (v.z + v.w);
-                ss[i >> 2] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+            float v[4] = {acc[i][0] + b, acc[i][1] + b, acc[i][2] + b, acc[i][3] + b};
+            float* o = out + (long)ch * plane + p;
+            if (vec && nvalid == 4) {
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (u < nvalid) o[u] = v[u];
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (u < nvalid) { s[i >> 2] += v[u]; ss[i >> 2] = fmaf(v[u], v[u], ss[i >> 2]); }
         }
 #pragma unroll
         for (int j = 0; j < NG; ++j) {
@@ -262,18 +286,25 @@ struct GnStatsEpilogue {
 // y = lrelu(acc + bias), stored NCHW.
 struct LreluEpilogue {
     static constexpr bool kAllowSmallTM = true;
-    const float* bias; float* out; long plane; float slope;
+    const float* bias; float* out; long plane; float slope; bool vec;
     template <int TM>
     __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
         if (p >= N) return;
+        const int nvalid = (N - p >= 4) ? 4 : (N - p);
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
             int ch = m0 + pg_channel<TM>(ty, i);
             if (ch >= M) continue;
             float b = __ldg(bias + ch);
-            float4 v = make_float4(lrelu(acc[i][0] + b, slope), lrelu(acc[i][1] + b, slope),
-                                   lrelu(acc[i][2] + b, slope), lrelu(acc[i][3] + b, slope));
-            *reinterpret_cast<float4*>(out + (long)ch * plane + p) = v;
+            float v[4] = {lrelu(acc[i][0] + b, slope), lrelu(acc[i][1] + b, slope),
+                          lrelu(acc[i][2] + b, slope), lrelu(acc[i][3] + b, slope)};
+            float* o = out + (long)ch * plane + p;
+            if (vec && nvalid == 4) {
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (u < nvalid) o[u] = v[u];
+            }
         }
     }
 };
@@ -302,11 +333,12 @@ struct LreluPoolEpilogue {
 struct DeconvEpilogue {
     static constexpr bool kAllowSmallTM = false;
     const float* bias; float* out; int W; float slope;   // W = input width; output plane = 4*H*W
-    long oplane;
+    long oplane; bool vec;                               // vec: W % 4 == 0 (a thread's 4 pixels share a row)
     template <int TM>
     __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
         static_assert(TM % 4 == 0, "deconv epilogue needs 4 consecutive rows per thread");
         if (p >= N) return;
+        const int nvalid = (N - p >= 4) ? 4 : (N - p);
         int y = p / W, x0 = p % W;
 #pragma unroll
         for (int j = 0; j < TM / 4; ++j) {
@@ -316,15 +348,23 @@ struct DeconvEpilogue {
             float b = __ldg(bias + co);
 #pragma unroll
             for (int dy = 0; dy < 2; ++dy) {
-                float* o = out + (long)co * oplane + (long)(2 * y + dy) * (2 * W) + 2 * x0;
                 const float* e = acc[j * 4 + dy * 2];       // dx = 0
                 const float* f = acc[j * 4 + dy * 2 + 1];   // dx = 1
-                float4 v0 = make_float4(lrelu(e[0] + b, slope), lrelu(f[0] + b, slope),
-                                        lrelu(e[1] + b, slope), lrelu(f[1] + b, slope));
-                float4 v1 = make_float4(lrelu(e[2] + b, slope), lrelu(f[2] + b, slope),
-                                        lrelu(e[3] + b, slope), lrelu(f[3] + b, slope));
-                *reinterpret_cast<float4*>(o) = v0;
-                *reinterpret_cast<float4*>(o + 4) = v1;
+                if (vec) {
+                    float* o = out + (long)co * oplane + (long)(2 * y + dy) * (2 * W) + 2 * x0;
+                    *reinterpret_cast<float4*>(o) = make_float4(lrelu(e[0] + b, slope), lrelu(f[0] + b, slope),
+                                                                lrelu(e[1] + b, slope), lrelu(f[1] + b, slope));
+                    *reinterpret_cast<float4*>(o + 4) = make_float4(lrelu(e[2] + b, slope), lrelu(f[2] + b, slope),
+                                                                    lrelu(e[3] + b, slope), lrelu(f[3] + b, slope));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (u >= nvalid) break;
+                        int q = p + u, yy = q / W, xx = q % W;
+                        float* o = out + (long)co * oplane + (long)(2 * yy + dy) * (2 * W) + 2 * xx;
+                        *reinterpret_cast<float2*>(o) = make_float2(lrelu(e[u] + b, slope), lrelu(f[u] + b, slope));
+                    }
+                }
             }
         }
     }

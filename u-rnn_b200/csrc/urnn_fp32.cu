@@ -36,22 +36,25 @@ __global__ void __launch_bounds__(256)
 cgru_blend_kernel(const float* __restrict__ G, const float* __restrict__ C, const float* __restrict__ h,
                   const float* __restrict__ sc1, const float* __restrict__ sh1,
                   const float* __restrict__ sc2, const float* __restrict__ sh2,
-                  float* __restrict__ h_out, int F, long nquad) {
+                  float* __restrict__ h_out, long N, long nquad) {
+    // flat over (channel, pixel) in quads; F*N is always a multiple of 4 (F % 32 == 0) but a quad may
+    // straddle two channels when N % 4 != 0
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)F * nquad) return;
-    int c = (int)(idx / nquad);
-    float a1 = __ldg(sc1 + c), b1 = __ldg(sh1 + c), a2 = __ldg(sc2 + c), b2 = __ldg(sh2 + c);
+    if (idx >= nquad) return;
     float4 g = __ldg(reinterpret_cast<const float4*>(G) + idx);
     float4 cc = __ldg(reinterpret_cast<const float4*>(C) + idx);
     float4 hv = __ldg(reinterpret_cast<const float4*>(h) + idx);
-    float4 o;
-    {
-        float z = sigmoid_acc(fmaf(g.x, a1, b1)), t = tanhf(fmaf(cc.x, a2, b2)); o.x = (1.f - z) * hv.x + z * t;
-        z = sigmoid_acc(fmaf(g.y, a1, b1)); t = tanhf(fmaf(cc.y, a2, b2)); o.y = (1.f - z) * hv.y + z * t;
-        z = sigmoid_acc(fmaf(g.z, a1, b1)); t = tanhf(fmaf(cc.z, a2, b2)); o.z = (1.f - z) * hv.z + z * t;
-        z = sigmoid_acc(fmaf(g.w, a1, b1)); t = tanhf(fmaf(cc.w, a2, b2)); o.w = (1.f - z) * hv.w + z * t;
+    const float gv[4] = {g.x, g.y, g.z, g.w}, cv[4] = {cc.x, cc.y, cc.z, cc.w}, hh[4] = {hv.x, hv.y, hv.z, hv.w};
+    float o[4];
+    int c0 = (int)((idx * 4) / N), c3 = (int)((idx * 4 + 3) / N);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        int c = (c0 == c3) ? c0 : (int)((idx * 4 + u) / N);
+        float a1 = __ldg(sc1 + c), b1 = __ldg(sh1 + c), a2 = __ldg(sc2 + c), b2 = __ldg(sh2 + c);
+        float z = sigmoid_acc(fmaf(gv[u], a1, b1)), t = tanhf(fmaf(cv[u], a2, b2));
+        o[u] = (1.f - z) * hh[u] + z * t;
     }
-    reinterpret_cast<float4*>(h_out)[idx] = o;
+    reinterpret_cast<float4*>(h_out)[idx] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 struct CellWs {
@@ -83,6 +86,8 @@ static size_t cell_ws_layout(const urnn_cell_desc* d, void* ws, size_t ws_bytes,
 
 size_t cgru_fwd_fp32_workspace(const urnn_cell_desc* d) { return cell_ws_layout(d, nullptr, 0, nullptr); }
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 template <class Loader>
 static void fill_segments(Loader& L, const urnn_cell_desc* d, const float* x, const float* e, const float* h) {
     int n = 0, acc = 0;
@@ -100,6 +105,7 @@ static void fill_segments(Loader& L, const urnn_cell_desc* d, const float* x, co
     }
     L.plane = (long)d->H * d->W;
     L.gate_pre = nullptr; L.gate_scale = nullptr; L.gate_shift = nullptr; L.gate_ch0 = 0;
+    L.vec = (L.plane % 4 == 0) && aligned16(x) && aligned16(e) && aligned16(h);
 }
 
 int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
@@ -116,11 +122,11 @@ int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
 
     GnStatsEpilogue ep1;
-    ep1.bias = p->b1; ep1.out = w.G; ep1.plane = N;
+    ep1.bias = p->b1; ep1.out = w.G; ep1.plane = N; ep1.vec = (N % 4 == 0);
     ep1.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx};
     ep1.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, 32.0 * (double)N, d->eps};
     GnStatsEpilogue ep2;
-    ep2.bias = p->b2; ep2.out = w.C; ep2.plane = N;
+    ep2.bias = p->b2; ep2.out = w.C; ep2.plane = N; ep2.vec = (N % 4 == 0);
     ep2.sink = StatSink{w.partial2, w.total2, w.counter + 1, F / 32, w.gx};
     ep2.aff = AffineOut{w.scale2, w.shift2, p->gn2_w, p->gn2_b, F, 32, 32.0 * (double)N, d->eps};
     AView A1{p->w1 + aoff, (long)Ktot * kk, 1};
@@ -138,10 +144,9 @@ int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
         L.gate_pre = w.G; L.gate_scale = w.scale1; L.gate_shift = w.shift1; L.gate_ch0 = F;
         URNN_TRY(launch_pixgemm(A2, F, Keff * kk, (int)N, L, ep2, true, st));
     }
-    long nquad = N / 4;
-    long total = (long)F * nquad;
-    cgru_blend_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.G, w.C, h, w.scale1, w.shift1, w.scale2,
-                                                                       w.shift2, h_out, F, nquad);
+    long nquad = (long)F * N / 4;
+    cgru_blend_kernel<<<(unsigned)((nquad + 255) / 256), 256, 0, st>>>(w.G, w.C, h, w.scale1, w.shift1, w.scale2,
+                                                                       w.shift2, h_out, N, nquad);
     URNN_LAUNCH_CHECK();
     return URNN_OK;
 }
@@ -155,7 +160,8 @@ int conv1x1_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, int pool, float slop
         L.src[0] = L.src[1] = L.src[2] = x; L.cnt[0] = Cin; L.cnt[1] = L.cnt[2] = 0;
         L.cend[0] = L.cend[1] = L.cend[2] = Cin; L.plane = (long)H * W;
         L.gate_pre = nullptr; L.gate_scale = nullptr; L.gate_shift = nullptr; L.gate_ch0 = 0;
-        LreluEpilogue ep{b, y, (long)H * W, slope};
+        L.vec = (L.plane % 4 == 0) && aligned16(x);
+        LreluEpilogue ep{b, y, (long)H * W, slope, (L.plane % 4 == 0) && aligned16(y)};
         return launch_pixgemm(A, Cout, Cin, H * W, L, ep, false, st);
     }
     QuadLoader L{x, (long)H * W, W, W / 2};
@@ -170,7 +176,8 @@ int deconv2x2_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, float slope, const
     L.src[0] = L.src[1] = L.src[2] = x; L.cnt[0] = Cin; L.cnt[1] = L.cnt[2] = 0;
     L.cend[0] = L.cend[1] = L.cend[2] = Cin; L.plane = (long)H * W;
     L.gate_pre = nullptr; L.gate_scale = nullptr; L.gate_shift = nullptr; L.gate_ch0 = 0;
-    DeconvEpilogue ep{b, y, W, slope, (long)4 * H * W};
+    L.vec = (L.plane % 4 == 0) && aligned16(x);
+    DeconvEpilogue ep{b, y, W, slope, (long)4 * H * W, (W % 4 == 0) && aligned16(y)};
     return launch_pixgemm(A, 4 * Cout, Cin, H * W, L, ep, false, st);
 }
 
