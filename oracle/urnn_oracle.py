@@ -28,13 +28,25 @@ LRELU_SLOPE = 0.2  # utils.py:63, head/network_blocks.py:39
 
 
 # --------------------------------------------------------------------------- primitives
-def conv2d_same(x, w, b=None):
+def round_bf16(a):
+    """Round to the nearest bfloat16 (ties to even), returned in the input dtype.  Used only to model the
+    URNN_MATH_BF16 mode of the CUDA path (operands of the gate contractions are rounded to bf16, products
+    and sums stay exact/fp32): the reference itself has no reduced-precision mode."""
+    f = np.ascontiguousarray(a, dtype=np.float32)
+    u = f.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).astype(a.dtype).reshape(a.shape)
+
+
+def conv2d_same(x, w, b=None, quant=None):
     """nn.Conv2d(stride 1, padding (k-1)//2) for odd k.  ConvRNN.py:95-96,101-102 (cells),
     utils.py:110-114 (stems, k=1), head/network_blocks.py:84-92,151-152.
     x (Cin,H,W), w (Cout,Cin,k,k), b (Cout,) or None -> (Cout,H,W)."""
     cout, cin, kh, kw = w.shape
     c, h, wd = x.shape
     assert c == cin and kh == kw and kh % 2 == 1
+    if quant == "bf16":
+        x, w = round_bf16(x), round_bf16(w)
     if kh == 1:
         y = (w[:, :, 0, 0] @ x.reshape(cin, h * wd)).reshape(cout, h, wd)
     else:
@@ -104,7 +116,7 @@ def conv_transpose2x2(x, w, b):
 
 
 # --------------------------------------------------------------------------- ConvGRU cell
-def cgru_cell_step(p, prefix, x, hidden, module, num_features):
+def cgru_cell_step(p, prefix, x, hidden, module, num_features, quant=None):
     """One time step of CGRU_cell.forward, ConvRNN.py:140-190.
 
     p[prefix + 'conv1.0.weight'] etc. are the cell's 8 tensors (ConvRNN.py:94-104).
@@ -121,7 +133,7 @@ def cgru_cell_step(p, prefix, x, hidden, module, num_features):
         cin = w1.shape[1] - hidden.shape[0]
         x = np.zeros((cin,) + hidden.shape[1:], dtype=hidden.dtype)
     combined_1 = np.concatenate([x, hidden], axis=0)                 # ConvRNN.py:153
-    gates_pre = conv2d_same(combined_1, w1, b1)
+    gates_pre = conv2d_same(combined_1, w1, b1, quant)
     gates = group_norm(gates_pre, (2 * F) // 32, g1w, g1b)           # ConvRNN.py:97
     z = sigmoid(gates[:F])                                           # ConvRNN.py:160-162
     r = sigmoid(gates[F:])
@@ -132,13 +144,13 @@ def cgru_cell_step(p, prefix, x, hidden, module, num_features):
         e, d = hidden[:F], hidden[F:]                                # ConvRNN.py:172
         combined_2 = np.concatenate([x, e, r * d], axis=0)           # ConvRNN.py:173
         prev = d
-    cand_pre = conv2d_same(combined_2, w2, b2)
+    cand_pre = conv2d_same(combined_2, w2, b2, quant)
     cand = np.tanh(group_norm(cand_pre, F // 32, g2w, g2b))          # ConvRNN.py:103,180
     h_next = (1 - z) * prev + z * cand                               # ConvRNN.py:185,189
     return h_next.astype(hidden.dtype), gates_pre, cand_pre
 
 
-def cgru_cell_forward(p, prefix, inputs, hidden, module, num_features, seq_len=1):
+def cgru_cell_forward(p, prefix, inputs, hidden, module, num_features, seq_len=1, quant=None):
     """CGRU_cell.forward over seq_len steps, ConvRNN.py:111-194: the encoder feeds h_t
     back as the next hidden state (ConvRNN.py:192); returns the stack (S,F,H,W).
     NB for the decoder variant the reference assigns the F-channel output to htprev, so
@@ -148,7 +160,7 @@ def cgru_cell_forward(p, prefix, inputs, hidden, module, num_features, seq_len=1
         assert seq_len == 1
     for t in range(seq_len):
         x = None if inputs is None else inputs[t]
-        hidden, _, _ = cgru_cell_step(p, prefix, x, hidden, module, num_features)
+        hidden, _, _ = cgru_cell_step(p, prefix, x, hidden, module, num_features, quant)
         outs.append(hidden)
     return np.stack(outs)
 
@@ -160,7 +172,7 @@ DEC_STEM_KEYS = {3: "decoder.stage3.deconv1_leaky_1", 2: "decoder.stage2.deconv2
                  1: "decoder.stage1.conv3_leaky_1"}
 
 
-def encoder_step(p, x, enc_states, down_factors=(1, 2, 2)):
+def encoder_step(p, x, enc_states, down_factors=(1, 2, 2), quant=None):
     """Encoder.forward / forward_by_stage for S=B=1, encoder.py:119-215.
     Stage k: 1x1 conv + LeakyReLU(0.2) [+ AvgPool2 AFTER the conv] -> ConvGRU
     (utils.py:85-121 layer order; net_params.py:82-88)."""
@@ -172,13 +184,13 @@ def encoder_step(p, x, enc_states, down_factors=(1, 2, 2)):
         if down_factors[k] > 1:
             cur = avg_pool2(cur)
         F = enc_states[k].shape[0]
-        h, _, _ = cgru_cell_step(p, f"encoder.rnn{k + 1}.", cur, enc_states[k], "encoder", F)
+        h, _, _ = cgru_cell_step(p, f"encoder.rnn{k + 1}.", cur, enc_states[k], "encoder", F, quant)
         new_states.append(h)
         cur = h
     return new_states
 
 
-def decoder_step(p, enc_states, dec_states):
+def decoder_step(p, enc_states, dec_states, quant=None):
     """Decoder.forward / forward_by_stage, decoder.py:102-217.  dec_states are ordered
     deepest-first (stage 3, 2, 1; decoder.py:194-212).  Returns (features (16,H,W), new states)."""
     new_states = []
@@ -188,7 +200,7 @@ def decoder_step(p, enc_states, dec_states):
         d = dec_states[idx]
         F = d.shape[0]
         hidden = np.concatenate([e, d], axis=0)                      # decoder.py:135
-        h, _, _ = cgru_cell_step(p, f"decoder.rnn{stage}.", cur, hidden, "decoder", F)
+        h, _, _ = cgru_cell_step(p, f"decoder.rnn{stage}.", cur, hidden, "decoder", F, quant)
         new_states.append(h)
         key = DEC_STEM_KEYS[stage]
         w, b = p[key + ".weight"], p[key + ".bias"]
@@ -219,12 +231,12 @@ def head_forward(p, feat, cls_thred=0.5):
 
 
 # --------------------------------------------------------------------------- whole step
-def ed_step(p, x, states, cls_thred=0.5):
+def ed_step(p, x, states, cls_thred=0.5, quant=None):
     """ED.forward for one time step, model.py:65-121.
     states = [e1,e2,e3,d(1/4),d(1/2),d(1x)] (general.py:50-95 order).
     Returns dict(out=(H,W) masked depth, prob, depth_raw, states=[6 new states])."""
-    enc = encoder_step(p, x, states[:3])
-    feat, dec = decoder_step(p, enc, states[3:])
+    enc = encoder_step(p, x, states[:3], quant=quant)
+    feat, dec = decoder_step(p, enc, states[3:], quant=quant)
     out, prob, raw = head_forward(p, feat, cls_thred)
     return {"out": out, "prob": prob, "depth_raw": raw, "states": list(enc) + list(dec), "feat": feat}
 
@@ -237,14 +249,14 @@ def zero_states(H, W, dtype=np.float32, enc_ch=(64, 96, 96), dec_ch=(96, 96, 64)
     return enc + dec
 
 
-def run_sequence(p, inputs, states=None, cls_thred=0.5):
+def run_sequence(p, inputs, states=None, cls_thred=0.5, quant=None):
     """The inference loop of test.py:356-367 without I/O: inputs (T,C,H,W) -> (T,H,W)."""
     T, _, H, W = inputs.shape
     if states is None:
         states = zero_states(H, W, inputs.dtype)
     outs = []
     for t in range(T):
-        res = ed_step(p, inputs[t], states, cls_thred)
+        res = ed_step(p, inputs[t], states, cls_thred, quant)
         states = res["states"]
         outs.append(res["out"])
     return np.stack(outs), states

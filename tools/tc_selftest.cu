@@ -1,0 +1,116 @@
+// tc_selftest.cu -- standalone bring-up harness for tc::gemm_gn_kernel (not part of the library).
+// Random problem, host reference with bf16-rounded operands, hang watchdog with per-role progress words.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+#include <unistd.h>
+#include <cstring>
+#include "../u-rnn_b200/csrc/tc_pixgemm.cuh"
+
+namespace urnn { void set_error(const char*, ...) {} void count_launch(int) {} }
+using namespace urnn;
+
+static float bf16r(float f) { return __bfloat162float(__float2bfloat16(f)); }
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
+    printf("== NOUT=%d K=%d N=%d segs=(%d,%d,%d)\n", NOUT, K, N, c0, c1, K - c0 - c1); fflush(stdout);
+    std::vector<float> hx((size_t)K * N), hw((size_t)NOUT * K), hb(NOUT), hg(NOUT, 1.f), hz(NOUT, 0.f);
+    srand(1);
+    for (auto& v : hx) v = (rand() / (float)RAND_MAX) * 2 - 1;
+    for (auto& v : hw) v = ((rand() / (float)RAND_MAX) * 2 - 1) * 0.2f;
+    for (auto& v : hb) v = (rand() / (float)RAND_MAX) - 0.5f;
+    float *dx, *dw, *db, *dout, *dgam, *dbet, *dsc, *dsh; float2* dpart; double2* dtot; unsigned* dcnt;
+    CK(cudaMalloc(&dx, hx.size() * 4)); CK(cudaMalloc(&dw, hw.size() * 4)); CK(cudaMalloc(&db, NOUT * 4));
+    CK(cudaMalloc(&dout, (size_t)NOUT * N * 4)); CK(cudaMalloc(&dgam, NOUT * 4)); CK(cudaMalloc(&dbet, NOUT * 4));
+    CK(cudaMalloc(&dsc, NOUT * 4)); CK(cudaMalloc(&dsh, NOUT * 4));
+    CK(cudaMalloc(&dpart, 8 * 4096 * sizeof(float2))); CK(cudaMalloc(&dtot, 8 * sizeof(double2))); CK(cudaMalloc(&dcnt, 256));
+    CK(cudaMemset(dcnt, 0, 256)); CK(cudaMemset(dout, 0, (size_t)NOUT * N * 4));
+    CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, hb.data(), NOUT * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dgam, hg.data(), NOUT * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbet, hz.data(), NOUT * 4, cudaMemcpyHostToDevice));
+    unsigned* hdbg; CK(cudaHostAlloc(&hdbg, 148 * 16 * 4, cudaHostAllocMapped));
+    memset(hdbg, 0, 148 * 16 * 4);
+    unsigned* ddbg; CK(cudaHostGetDevicePointer(&ddbg, hdbg, 0));
+
+    std::vector<float> hgp((size_t)(K - c0) * 2 * N), hgs(2 * K, 0.7f), hgh(2 * K, 0.1f);
+    for (auto& v : hgp) v = (rand() / (float)RAND_MAX) * 4 - 2;
+    float *dgp, *dgs, *dgh;
+    CK(cudaMalloc(&dgp, hgp.size() * 4)); CK(cudaMalloc(&dgs, hgs.size() * 4)); CK(cudaMalloc(&dgh, hgh.size() * 4));
+    CK(cudaMemcpy(dgp, hgp.data(), hgp.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dgs, hgs.data(), hgs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dgh, hgh.data(), hgh.size() * 4, cudaMemcpyHostToDevice));
+    tc::GemmParams P;
+    P.seg.src[0] = dx; P.seg.src[1] = dx + (size_t)c0 * N; P.seg.src[2] = dx + (size_t)(c0 + c1) * N;
+    P.seg.cend[0] = c0; P.seg.cend[1] = c0 + c1; P.seg.cend[2] = K;
+    P.seg.plane = N; P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
+    const int gseg = (K - c0 - c1 > 0) ? 2 : 1; const int glen = (gseg == 2) ? K - c0 - c1 : c1; const int gk0 = K - glen;
+    if (gated) { P.seg.gate_seg = gseg; P.seg.gate_ch0 = glen; P.seg.gate_pre = dgp; P.seg.gate_scale = dgs; P.seg.gate_shift = dgh; }
+    P.W = dw; P.w_ld = K; P.bias = db; P.NOUT = NOUT; P.K = K; P.N = N; P.out = dout; P.out_plane = N;
+    int ntiles = (N + 127) / 128, grid = ntiles < 148 ? ntiles : 148;
+    P.sink = StatSink{dpart, dtot, dcnt, NOUT / 32, 4096};
+    P.aff = AffineOut{dsc, dsh, dgam, dbet, NOUT, 32, 32.0 * N, 1e-5f};
+    int ns = 0; size_t smem = tc::gemm_smem_bytes(NOUT, K, &ns);
+    P.nstage = ns; int cols = 32; while (cols < 2 * NOUT) cols <<= 1; P.tmem_cols = cols; P.dbg = ddbg;
+    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+    printf("grid=%d smem=%zu nstage=%d tmem_cols=%d\n", grid, smem, ns, cols); fflush(stdout);
+    cudaEvent_t ev; CK(cudaEventCreate(&ev));
+    tc::gemm_gn_kernel<<<grid, tc::NTHREADS, smem>>>(P);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev));
+    auto t0 = std::chrono::steady_clock::now();
+    while (cudaEventQuery(ev) == cudaErrorNotReady) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) {
+            printf("HANG: progress words of CTA 0..%d\n", grid < 4 ? grid - 1 : 3);
+            for (int c = 0; c < (grid < 4 ? grid : 4); ++c) {
+                printf(" cta %d:", c);
+                for (int i = 0; i < 15; ++i) printf(" %x", hdbg[c * 16 + i]);
+                printf("\n");
+            }
+            fflush(stdout);
+            _exit(3);
+        }
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("kernel error: %s\n", cudaGetErrorString(e)); printf(" cta0:"); for (int i = 0; i < 15; ++i) printf(" %x", hdbg[i]); printf("\n"); return 2; }
+    std::vector<float> ho((size_t)NOUT * N);
+    CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0; long bad = 0;
+    std::vector<float> xr(hx.size()), wr(hw.size());
+    for (size_t i = 0; i < hx.size(); ++i) {
+        float v = hx[i]; int k = (int)(i / N); int p = (int)(i % N);
+        if (gated && k >= gk0) { float g = hgp[(size_t)(glen + k - gk0) * N + p]; v *= 1.0f / (1.0f + expf(-(g * 0.7f + 0.1f))); }
+        xr[i] = bf16r(v);
+    }
+    for (size_t i = 0; i < hw.size(); ++i) wr[i] = bf16r(hw[i]);
+    int step = N > 4096 ? N / 2048 : 1;
+    for (int n = 0; n < NOUT; ++n)
+        for (int p = 0; p < N; p += step) {
+            double a = hb[n];
+            for (int k = 0; k < K; ++k) a += (double)wr[(size_t)n * K + k] * xr[(size_t)k * N + p];
+            double d = fabs(a - ho[(size_t)n * N + p]);
+            if (d > maxerr) maxerr = d;
+            if (d > 1e-3) { if (bad < 5) printf("  mismatch n=%d p=%d ref=%f got=%f\n", n, p, a, ho[(size_t)n * N + p]); ++bad; }
+        }
+    printf("max abs err %.3e, mismatches %ld -> %s\n", maxerr, bad, bad ? "FAIL" : "ok"); fflush(stdout);
+    return bad ? 1 : 0;
+}
+
+int main() {
+    int rc = 0;
+    rc |= run(128, 80, 256, 16, 64);
+    rc |= run(64, 80, 256, 16, 64, true);
+    rc |= run(96, 288, 62500, 96, 96, true);
+    rc |= run(128, 80, 100, 16, 64);
+    rc |= run(64, 64, 128 * 5, 0, 0);
+    rc |= run(192, 288, 128 * 300, 96, 96);
+    rc |= run(96, 200, 15625, 8, 96);
+    rc |= run(128, 224, 250000, 96, 64);
+    return rc;
+}

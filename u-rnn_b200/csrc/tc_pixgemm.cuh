@@ -1,0 +1,324 @@
+// tc_pixgemm.cuh -- tcgen05 "pixel GEMM" for sm_100a:  D[128 pixels x NOUT] = X^T[128 x K] * W^T[K x NOUT]
+// with bf16 operands (rounded on the fly from fp32 NCHW maps) and fp32 accumulation in tensor memory.
+//
+// One persistent CTA per SM, 9 warps, warp-specialised:
+//   warps 0-3  epilogue : tcgen05.ld the accumulator (TMEM lane = pixel, column = output channel), fused epilogue
+//   warps 4-7  producers: thread = pixel; coalesced fp32 loads of the (virtually concatenated, optionally
+//                         reset-gated) input channels -> bf16 -> 128B-swizzled K-major shared-memory tile
+//   warp  8    MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=NOUT, K=16 per instruction
+// Pipelines: K-block ring in shared memory (full/empty mbarriers, producer -> MMA) and a double-buffered
+// accumulator in TMEM (tmem_full/tmem_empty mbarriers, MMA -> epilogue), so loads, MMAs and epilogues of
+// successive 128-pixel tiles overlap.  Weights are converted once per CTA and stay resident in shared memory.
+//
+// The activations pass through registers because they must be rounded fp32 -> bf16 (and, for the candidate
+// GEMM, multiplied by the reset gate) before the tensor core sees them; TMA cannot do either, so the
+// producer is SIMT and publishes its stores to the async proxy with fence.proxy.async.
+#pragma once
+#include <cuda_bf16.h>
+#include "urnn_common.cuh"
+
+namespace urnn {
+namespace tc {
+
+constexpr int TILE_M = 128;           // pixels per tile (TMEM lanes)
+constexpr int KBLK = 64;              // bf16 elements per 128-byte swizzle row
+constexpr int STAGE_BYTES = TILE_M * 128;
+constexpr int NTHREADS = 288;
+constexpr int MAXG = 8;
+constexpr size_t SMEM_CAP = 229376;  // dynamic shared memory budget (227 KB opt-in limit minus static use)               // NOUT <= 256 -> at most 8 GroupNorm groups per tile row
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=nout
+__device__ __forceinline__ uint32_t instr_desc_bf16(int nout) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---------------------------------------------------------------------------------------------- parameters
+// Virtual channel concatenation of up to three fp32 NCHW sources; the segment `gate_seg` (or none: -1) is
+// multiplied by sigmoid(gate_pre[gate_ch0 + c] * gate_scale[..] + gate_shift[..]) (the reset gate).
+struct Segs {
+    const float* src[3]; int cend[3];
+    long plane;
+    int gate_seg; int gate_ch0;
+    const float* gate_pre; const float* gate_scale; const float* gate_shift;
+};
+
+struct GemmParams {
+    Segs seg;
+    const float* W; long w_ld;        // weights W[n * w_ld + k], n < NOUT, k < K (fp32, converted per CTA)
+    const float* bias;                // [NOUT]
+    int NOUT, K, N;                   // output channels (multiple of 32, <= 256), reduction size, pixels
+    float* out; long out_plane;       // fp32 NCHW destination of (acc + bias)
+    StatSink sink; AffineOut aff;     // GroupNorm statistics of the destination (32 channels per set)
+    int nstage;                       // K-block ring depth
+    int tmem_cols;                    // power of two >= 2 * NOUT
+    volatile unsigned* dbg;           // optional host-mapped progress words (bring-up only), else nullptr
+};
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;           // swizzle atoms need 1024-byte alignment
+    uint8_t* sm = smem_raw + (base - raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NOUT = P.NOUT, K = P.K, N = P.N;
+    const int Kp = (K + 15) & ~15;                          // padded to the MMA K
+    const int nkb = (Kp + KBLK - 1) / KBLK;                 // K blocks per tile
+    const int last_k = Kp - (nkb - 1) * KBLK;               // valid (padded) columns in the last block
+    const int wblk_bytes = NOUT * 128;
+    const uint32_t w_off = 0;
+    const uint32_t a_off = w_off + (uint32_t)nkb * wblk_bytes;
+    const uint32_t bias_off = a_off + (uint32_t)P.nstage * STAGE_BYTES;
+    const uint32_t bar_off = bias_off + 1024;
+    // barriers: full[nstage], empty[nstage], tmem_full[2], tmem_empty[2]
+    const uint32_t full0 = base + bar_off, empty0 = full0 + 8 * P.nstage;
+    const uint32_t tfull0 = empty0 + 8 * P.nstage, tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + bar_off + 16 * P.nstage + 32);
+    float* sbias = reinterpret_cast<float*>(sm + bias_off);
+    __shared__ float red[2][4][MAXG];
+
+    // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
+    if (tid == 0) {
+        for (int s = 0; s < P.nstage; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+    for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = __ldg(P.bias + i);
+    {
+        const int chunks_per_row = nkb * 8;                 // 16-byte chunks (8 bf16) per weight row
+        for (int idx = tid; idx < NOUT * chunks_per_row; idx += NTHREADS) {
+            int n = idx / chunks_per_row, ch = idx % chunks_per_row;
+            int kb = ch >> 3, j = ch & 7, k0 = kb * KBLK + j * 8;
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < K) ? __ldg(P.W + (long)n * P.w_ld + k0 + u) : 0.f;
+            uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(sm + w_off + kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+#define TC_DBG(slot, val) do { if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 16 + (slot)] = (val); } while (0)
+    TC_DBG(0, 0x100u | tmem_base);
+    const int ntiles = (N + TILE_M - 1) / TILE_M;
+    const int acc_stride = P.tmem_cols >> 1;                // columns per accumulator stage
+
+    float st_s[MAXG], st_ss[MAXG];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) { st_s[g] = 0.f; st_ss[g] = 0.f; }
+
+    if (warp >= 4 && warp < 8) {
+        // =========================================================================== producers
+        const int pr = tid - 128;                            // row of the tile = pixel
+        int stage = 0; uint32_t phase = 0;
+        const Segs& S = P.seg;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long p = (long)tile * TILE_M + pr;
+            const bool valid = p < N;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                uint8_t* row = sm + a_off + stage * STAGE_BYTES + pr * 128;
+                const int nchunk = ((kb == nkb - 1) ? last_k : KBLK) >> 3;
+                for (int j = 0; j < nchunk; ++j) {
+                    float v[8];
+                    const int k0 = kb * KBLK + j * 8;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 + u;
+                        float x = 0.f;
+                        if (valid && k < K) {
+                            const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
+                            const int c = k - (sg == 0 ? 0 : S.cend[sg - 1]);
+                            x = __ldg(S.src[sg] + (long)c * S.plane + p);
+                            if (sg == S.gate_seg) {
+                                const int gc = S.gate_ch0 + c;
+                                const float g = __ldg(S.gate_pre + (long)gc * S.plane + p);
+                                x *= sigmoid_acc(fmaf(g, __ldg(S.gate_scale + gc), __ldg(S.gate_shift + gc)));
+                            }
+                        }
+                        v[u] = x;
+                    }
+                    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    *reinterpret_cast<uint4*>(row + ((j ^ (pr & 7)) << 4)) = pk;
+                }
+                fence_proxy_async();                         // generic-proxy stores -> visible to tcgen05.mma
+                mbar_arrive(full0 + 8 * stage);
+                TC_DBG(1 + (warp - 4), (unsigned)(tile * 100 + kb + 1));
+                if (++stage == P.nstage) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 8) {
+        // =========================================================================== MMA issuer
+        // every lane follows the pipeline (waits), lane 0 alone issues tcgen05.mma / tcgen05.commit
+        const uint32_t idesc = instr_desc_bf16(NOUT);
+        int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(tempty0 + 8 * as, aphase ^ 1);         // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_stride);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full0 + 8 * stage, phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = base + a_off + stage * STAGE_BYTES;
+                    const uint32_t b_addr = base + w_off + kb * wblk_bytes;
+                    const int nmma = ((kb == nkb - 1) ? last_k : KBLK) >> 4;
+                    for (int j = 0; j < nmma; ++j)
+                        umma_f16(d_tmem, smem_desc_sw128(a_addr + j * 32), smem_desc_sw128(b_addr + j * 32), idesc,
+                                 (kb | j) ? 1u : 0u);
+                    umma_commit(empty0 + 8 * stage);         // frees the ring slot when these MMAs retire
+                }
+                __syncwarp();
+                TC_DBG(5, (unsigned)(tile * 100 + kb + 1));
+                if (++stage == P.nstage) { stage = 0; phase ^= 1; }
+            }
+            if (lane == 0) umma_commit(tfull0 + 8 * as);     // accumulator complete -> epilogue
+            __syncwarp();
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+    } else {
+        // =========================================================================== epilogue (warps 0-3)
+        int as = 0; uint32_t aphase = 0;
+        const int ng = NOUT >> 5;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long p = (long)tile * TILE_M + tid;        // TMEM lane = tid (warp w owns lanes 32w..32w+31)
+            const bool valid = p < N;
+            mbar_wait(tfull0 + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * acc_stride);
+#pragma unroll
+            for (int g = 0; g < MAXG; ++g) {
+                if (g < ng) {
+                    float v[32];
+                    tmem_ld32(t_addr + g * 32, v);
+                    float s = 0.f, ss = 0.f;
+                    float* o = P.out + (long)(g * 32) * P.out_plane + p;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float y = v[i] + sbias[g * 32 + i];
+                        if (valid) { o[(long)i * P.out_plane] = y; s += y; ss = fmaf(y, y, ss); }
+                    }
+                    st_s[g] += s; st_ss[g] += ss;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * as);
+            TC_DBG(6 + warp, (unsigned)(tile + 1));
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+        // per-CTA GroupNorm partials (fixed order: lanes -> warps -> CTA)
+#pragma unroll
+        for (int g = 0; g < MAXG; ++g) {
+            if (g < ng) {
+                float a = warp_sum(st_s[g]), b = warp_sum(st_ss[g]);
+                if (lane == 0) { red[0][warp][g] = a; red[1][warp][g] = b; }
+            }
+        }
+    }
+    tc_fence_before();
+    TC_DBG(10 + (warp > 4 ? 4 : warp), 0xD0u);
+    __syncthreads();
+    if (tid < (NOUT >> 5)) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { a += red[0][w][tid]; b += red[1][w][tid]; }
+        P.sink.partial[(size_t)tid * P.sink.stride + blockIdx.x] = make_float2(a, b);
+    }
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
+    stats_finalize_last_cta(P.sink, gridDim.x, gridDim.x, &P.aff);
+}
+
+// dynamic shared memory needed for a given problem; 0 if it cannot fit
+static inline size_t gemm_smem_bytes(int NOUT, int K, int* nstage_out) {
+    const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
+    const size_t fixed = 1024 /*align slack*/ + (size_t)nkb * NOUT * 128 + 1024 /*bias*/ + 512 /*barriers*/;
+    const size_t cap = SMEM_CAP;
+    if (fixed + 2 * STAGE_BYTES > cap) return 0;
+    int ns = (int)((cap - fixed) / STAGE_BYTES);
+    if (ns > 8) ns = 8;
+    if (nstage_out) *nstage_out = ns;
+    return fixed + (size_t)ns * STAGE_BYTES;
+}
+
+}  // namespace tc
+}  // namespace urnn

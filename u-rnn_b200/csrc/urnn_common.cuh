@@ -84,7 +84,7 @@ struct AffineOut {
 __device__ __forceinline__ void stats_finalize_last_cta(const StatSink& s, int ncontrib, unsigned ncta_total,
                                                         const AffineOut* aff) {
     __shared__ bool is_last;
-    __shared__ double red[2][8];
+    __shared__ double red[2][32];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -57,13 +57,7 @@ cgru_blend_kernel(const float* __restrict__ G, const float* __restrict__ C, cons
     reinterpret_cast<float4*>(h_out)[idx] = make_float4(o[0], o[1], o[2], o[3]);
 }
 
-struct CellWs {
-    float *G, *C, *scale1, *shift1, *scale2, *shift2;
-    float2 *partial1, *partial2;
-    double2 *total1, *total2;
-    unsigned* counter;
-    int gx;
-};
+typedef CellWsView CellWs;
 
 static size_t cell_ws_layout(const urnn_cell_desc* d, void* ws, size_t ws_bytes, CellWs* out) {
     long N = (long)d->H * d->W;
@@ -85,6 +79,15 @@ static size_t cell_ws_layout(const urnn_cell_desc* d, void* ws, size_t ws_bytes,
 }
 
 size_t cgru_fwd_fp32_workspace(const urnn_cell_desc* d) { return cell_ws_layout(d, nullptr, 0, nullptr); }
+size_t cell_ws_view(const urnn_cell_desc* d, void* ws, size_t ws_bytes, CellWsView* out) { return cell_ws_layout(d, ws, ws_bytes, out); }
+
+int cgru_blend_launch(const CellWsView& w, const float* h, float* h_out, int F, long N, cudaStream_t st) {
+    long nquad = (long)F * N / 4;
+    cgru_blend_kernel<<<(unsigned)((nquad + 255) / 256), 256, 0, st>>>(w.G, w.C, h, w.scale1, w.shift1, w.scale2,
+                                                                       w.shift2, h_out, N, nquad);
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -144,11 +147,7 @@ int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
         L.gate_pre = w.G; L.gate_scale = w.scale1; L.gate_shift = w.shift1; L.gate_ch0 = F;
         URNN_TRY(launch_pixgemm(A2, F, Keff * kk, (int)N, L, ep2, true, st));
     }
-    long nquad = (long)F * N / 4;
-    cgru_blend_kernel<<<(unsigned)((nquad + 255) / 256), 256, 0, st>>>(w.G, w.C, h, w.scale1, w.shift1, w.scale2,
-                                                                       w.shift2, h_out, N, nquad);
-    URNN_LAUNCH_CHECK();
-    return URNN_OK;
+    return cgru_blend_launch(w, h, h_out, F, N, st);
 }
 
 // ------------------------------------------------------------------------------------------------ stems

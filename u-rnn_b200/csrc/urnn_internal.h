@@ -5,6 +5,21 @@
 
 namespace urnn {
 
+// per-cell workspace view shared by the fp32 and tcgen05 paths
+struct CellWsView {
+    float *G, *C, *scale1, *shift1, *scale2, *shift2;   // pre-GN gate / candidate maps, folded GN affines
+    float2 *partial1, *partial2;
+    double2 *total1, *total2;
+    unsigned* counter;
+    int gx;                                            // partial stride (>= CTAs of any producer kernel)
+};
+size_t cell_ws_view(const urnn_cell_desc* d, void* ws, size_t ws_bytes, CellWsView* out);
+int cgru_blend_launch(const CellWsView& w, const float* h, float* h_out, int F, long N, cudaStream_t st);
+
+// tcgen05 bf16 path (cgru_tc.cu)
+int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // fp32 FFMA path (urnn_fp32.cu)
 size_t cgru_fwd_fp32_workspace(const urnn_cell_desc* d);
 int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,

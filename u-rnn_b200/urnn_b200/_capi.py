@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liburnn_b200.so")
+LIB_PATH = os.environ.get("URNN_B200_LIB", os.path.join(HERE, "liburnn_b200.so"))   # override: bring-up only
 
 URNN_CELL_ENCODER, URNN_CELL_DECODER = 0, 1
 MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
