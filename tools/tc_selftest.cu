@@ -34,8 +34,8 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     CK(cudaMemcpy(db, hb.data(), NOUT * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgam, hg.data(), NOUT * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dbet, hz.data(), NOUT * 4, cudaMemcpyHostToDevice));
-    unsigned* hdbg; CK(cudaHostAlloc(&hdbg, 148 * 16 * 4, cudaHostAllocMapped));
-    memset(hdbg, 0, 148 * 16 * 4);
+    unsigned* hdbg; CK(cudaHostAlloc(&hdbg, (148 * 16 + 6 * 64) * 4, cudaHostAllocMapped));
+    memset(hdbg, 0, (148 * 16 + 6 * 64) * 4);
     unsigned* ddbg; CK(cudaHostGetDevicePointer(&ddbg, hdbg, 0));
 
     std::vector<float> hgp((size_t)(K - c0) * 2 * N), hgs(2 * K, 0.7f), hgh(2 * K, 0.1f);
@@ -48,7 +48,7 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     tc::GemmParams P;
     P.seg.src[0] = dx; P.seg.src[1] = dx + (size_t)c0 * N; P.seg.src[2] = dx + (size_t)(c0 + c1) * N;
     P.seg.cend[0] = c0; P.seg.cend[1] = c0 + c1; P.seg.cend[2] = K;
-    P.seg.plane = N; P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
+    P.seg.vec = (N % 4 == 0); P.seg.plane = N; P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
     const int gseg = (K - c0 - c1 > 0) ? 2 : 1; const int glen = (gseg == 2) ? K - c0 - c1 : c1; const int gk0 = K - glen;
     if (gated) { P.seg.gate_seg = gseg; P.seg.gate_ch0 = glen; P.seg.gate_pre = dgp; P.seg.gate_scale = dgs; P.seg.gate_shift = dgh; }
     P.W = dw; P.w_ld = K; P.bias = db; P.NOUT = NOUT; P.K = K; P.N = N; P.out = dout; P.out_plane = N;
@@ -57,10 +57,11 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     P.aff = AffineOut{dsc, dsh, dgam, dbet, NOUT, 32, 32.0 * N, 1e-5f};
     int ns = 0; size_t smem = tc::gemm_smem_bytes(NOUT, K, &ns);
     P.nstage = ns; int cols = 32; while (cols < 2 * NOUT) cols <<= 1; P.tmem_cols = cols; P.dbg = ddbg;
-    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
     printf("grid=%d smem=%zu nstage=%d tmem_cols=%d\n", grid, smem, ns, cols); fflush(stdout);
     cudaEvent_t ev; CK(cudaEventCreate(&ev));
-    tc::gemm_gn_kernel<<<grid, tc::NTHREADS, smem>>>(P);
+    if (gated) tc::gemm_gn_kernel<true><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false><<<grid, tc::NTHREADS, smem>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev));
     auto t0 = std::chrono::steady_clock::now();
@@ -99,6 +100,21 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
             if (d > 1e-3) { if (bad < 5) printf("  mismatch n=%d p=%d ref=%f got=%f\n", n, p, a, ho[(size_t)n * N + p]); ++bad; }
         }
     printf("max abs err %.3e, mismatches %ld -> %s\n", maxerr, bad, bad ? "FAIL" : "ok"); fflush(stdout);
+    if (N >= 60000) {
+        const unsigned* tr = hdbg + 148 * 16; unsigned t0 = tr[0];
+        printf("trace (us since setup done): kernel end %.1f\n", (tr[5 * 64] - t0) * 1e-3);
+        for (int i = 0; i < 16; ++i)
+            printf("  tile %2d: prod_done %7.1f  mma_issued %7.1f  epi_start %7.1f  epi_end %7.1f\n", i, (tr[64 + i] - t0) * 1e-3,
+                   (tr[128 + i] - t0) * 1e-3, (tr[192 + i] - t0) * 1e-3, (tr[256 + i] - t0) * 1e-3);
+        cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        P.dbg = nullptr;
+        CK(cudaEventRecord(a));
+        for (int i = 0; i < 10; ++i) { if (gated) tc::gemm_gn_kernel<true><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false><<<grid, tc::NTHREADS, smem>>>(P); }
+        CK(cudaEventRecord(b)); CK(cudaDeviceSynchronize());
+        float ms; CK(cudaEventElapsedTime(&ms, a, b));
+        double us = ms * 100.0, bytes = ((double)K + NOUT) * N * 4;
+        printf("time %.1f us/launch, %.0f GB/s (in+out fp32)\n", us, bytes / us * 1e-3); fflush(stdout);
+    }
     return bad ? 1 : 0;
 }
 

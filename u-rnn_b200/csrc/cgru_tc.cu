@@ -9,7 +9,7 @@
 namespace urnn {
 
 static int g_num_sms = 0;
-static bool g_attr_set = false;
+static bool g_attr_set[2] = {false, false};
 
 static int tc_launch(tc::GemmParams& P, cudaStream_t st) {
     if (g_num_sms == 0) {
@@ -17,9 +17,11 @@ static int tc_launch(tc::GemmParams& P, cudaStream_t st) {
         URNN_CUDA(cudaGetDevice(&dev));
         URNN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    if (!g_attr_set) {
-        URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
-        g_attr_set = true;
+    const bool gated = P.seg.gate_seg >= 0;
+    if (!g_attr_set[gated]) {
+        if (gated) URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+        else       URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+        g_attr_set[gated] = true;
     }
     TRACE("tc_launch: NOUT=%d K=%d N=%d sms=%d\n", P.NOUT, P.K, P.N, g_num_sms);
     int nstage = 0;
@@ -32,7 +34,8 @@ static int tc_launch(tc::GemmParams& P, cudaStream_t st) {
     int ntiles = (P.N + tc::TILE_M - 1) / tc::TILE_M;
     int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
     TRACE("tc_launch: grid=%d smem=%zu nstage=%d cols=%d\n", grid, smem, nstage, cols);
-    tc::gemm_gn_kernel<<<grid, tc::NTHREADS, smem, st>>>(P);
+    if (gated) tc::gemm_gn_kernel<true><<<grid, tc::NTHREADS, smem, st>>>(P);
+    else       tc::gemm_gn_kernel<false><<<grid, tc::NTHREADS, smem, st>>>(P);
     URNN_LAUNCH_CHECK();
     TRACE("tc_launch: launched\n");
     return URNN_OK;
@@ -66,6 +69,7 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     int acc = 0;
     for (int i = 0; i < 3; ++i) { P.seg.src[i] = srcs[i]; acc += cnt[i]; P.seg.cend[i] = acc; }
     P.seg.plane = N;
+    P.seg.vec = (N % 4 == 0) && ((((uintptr_t)x | (uintptr_t)e | (uintptr_t)h | (uintptr_t)w.G) & 15) == 0);
     P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
     P.N = (int)N; P.K = Keff; P.w_ld = Ktot;
 

@@ -1,11 +1,11 @@
 // tc_pixgemm.cuh -- tcgen05 "pixel GEMM" for sm_100a:  D[128 pixels x NOUT] = X^T[128 x K] * W^T[K x NOUT]
 // with bf16 operands (rounded on the fly from fp32 NCHW maps) and fp32 accumulation in tensor memory.
 //
-// One persistent CTA per SM, 9 warps, warp-specialised:
-//   warps 0-3  epilogue : tcgen05.ld the accumulator (TMEM lane = pixel, column = output channel), fused epilogue
-//   warps 4-7  producers: thread = pixel; coalesced fp32 loads of the (virtually concatenated, optionally
+// One persistent CTA per SM, 25 warps, warp-specialised:
+//   warps 0-7  epilogue : tcgen05.ld the accumulator (TMEM lane = pixel, column = output channel), fused epilogue
+//   warps 8-23 producers: 4 threads per pixel, software-pipelined two K blocks deep; coalesced fp32 loads of the (virtually concatenated, optionally
 //                         reset-gated) input channels -> bf16 -> 128B-swizzled K-major shared-memory tile
-//   warp  8    MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=NOUT, K=16 per instruction
+//   warp  24   MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=NOUT, K=16 per instruction
 // Pipelines: K-block ring in shared memory (full/empty mbarriers, producer -> MMA) and a double-buffered
 // accumulator in TMEM (tmem_full/tmem_empty mbarriers, MMA -> epilogue), so loads, MMAs and epilogues of
 // successive 128-pixel tiles overlap.  Weights are converted once per CTA and stay resident in shared memory.
@@ -23,7 +23,10 @@ namespace tc {
 constexpr int TILE_M = 128;           // pixels per tile (TMEM lanes)
 constexpr int KBLK = 64;              // bf16 elements per 128-byte swizzle row
 constexpr int STAGE_BYTES = TILE_M * 128;
-constexpr int NTHREADS = 288;
+constexpr int NPROD = 512;            // producer threads: 4 per tile row (each takes 2 of a K block's 8 chunks)
+constexpr int NEPI = 256;             // epilogue threads: warp w owns TMEM lanes 32*(w%4).. and column half w/4
+constexpr int NTHREADS = NEPI + NPROD + 32;
+constexpr int MMA_WARP = (NEPI + NPROD) / 32;
 constexpr int MAXG = 8;
 constexpr size_t SMEM_CAP = 229376;  // dynamic shared memory budget (227 KB opt-in limit minus static use)               // NOUT <= 256 -> at most 8 GroupNorm groups per tile row
 
@@ -97,9 +100,20 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=nout
+// MN-major (pixel-contiguous) A tile, 128-byte swizzle: 1024-byte atoms of 8 K-rows x 64 MN elements;
+// leading byte offset = distance between atoms along MN (8192), stride byte offset = along K (1024).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A bf16 MN-major, B bf16 K-major, M=128, N=nout
 __device__ __forceinline__ uint32_t instr_desc_bf16(int nout) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(nout >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -114,6 +128,7 @@ struct Segs {
     const float* src[3]; int cend[3];
     long plane;
     int gate_seg; int gate_ch0;
+    bool vec;                      // plane % 4 == 0 and every source 16-byte aligned: float4 loads
     const float* gate_pre; const float* gate_scale; const float* gate_shift;
 };
 
@@ -130,6 +145,7 @@ struct GemmParams {
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
+template <bool GATED>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -151,15 +167,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const uint32_t tfull0 = empty0 + 8 * P.nstage, tempty0 = tfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + bar_off + 16 * P.nstage + 32);
     float* sbias = reinterpret_cast<float*>(sm + bias_off);
-    __shared__ float red[2][4][MAXG];
+    __shared__ float red[2][4][MAXG];   // [sum|sumsq][lane quarter][group]; each (quarter, group) has one owner warp
 
     // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
     if (tid == 0) {
-        for (int s = 0; s < P.nstage; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 128); }
+        for (int s = 0; s < P.nstage; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NEPI); }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
     for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = __ldg(P.bias + i);
     {
         const int chunks_per_row = nkb * 8;                 // 16-byte chunks (8 bf16) per weight row
@@ -180,54 +196,125 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const uint32_t tmem_base = *tmem_slot;
 #define TC_DBG(slot, val) do { if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 16 + (slot)] = (val); } while (0)
     TC_DBG(0, 0x100u | tmem_base);
+#define TC_TRACE(role, idx) do { if (P.dbg && blockIdx.x == 0 && (tid & 31) == 0 && (idx) < 64) { unsigned t_; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_)); P.dbg[148 * 16 + (role) * 64 + (idx)] = t_; } } while (0)
+    TC_TRACE(0, 0);
     const int ntiles = (N + TILE_M - 1) / TILE_M;
     const int acc_stride = P.tmem_cols >> 1;                // columns per accumulator stage
 
-    float st_s[MAXG], st_ss[MAXG];
+    float st_s[MAXG / 2], st_ss[MAXG / 2];
 #pragma unroll
-    for (int g = 0; g < MAXG; ++g) { st_s[g] = 0.f; st_ss[g] = 0.f; }
+    for (int g = 0; g < MAXG / 2; ++g) { st_s[g] = 0.f; st_ss[g] = 0.f; }
 
-    if (warp >= 4 && warp < 8) {
+    if (warp >= NEPI / 32 && warp < MMA_WARP) {
         // =========================================================================== producers
-        const int pr = tid - 128;                            // row of the tile = pixel
-        int stage = 0; uint32_t phase = 0;
+        // The A tile is stored MN-major (pixel-contiguous), exactly like the NCHW source: a thread moves 8
+        // consecutive pixels of one channel (two 16-byte global loads -> 8 bf16 -> one 16-byte shared store), a
+        // half-warp covers the 512 contiguous bytes a channel contributes to the tile.  Units (tile, K block) are
+        // streamed two deep: the loads of unit u+1 are issued before unit u is converted and stored.
+        // Shared layout of a stage (canonical UMMA MN-major, SWIZZLE_128B): 1024-byte atoms of 8 channels x 64
+        // pixels; atom(mblk, kblk) at mblk*8192 + kblk*1024; inside: channel (k&7)*128 B, 16-byte chunk j = (pixel%64)/8
+        // stored at chunk position j ^ (k&7).
+        const int pt = tid - NEPI;
         const Segs& S = P.seg;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long p = (long)tile * TILE_M + pr;
-            const bool valid = p < N;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                uint8_t* row = sm + a_off + stage * STAGE_BYTES + pr * 128;
-                const int nchunk = ((kb == nkb - 1) ? last_k : KBLK) >> 3;
-                for (int j = 0; j < nchunk; ++j) {
-                    float v[8];
-                    const int k0 = kb * KBLK + j * 8;
+        struct Buf { float v[2][8]; float g[GATED ? 2 : 1][GATED ? 8 : 1]; int gch[2]; };
+        int trace_i = 0;
+
+        auto issue = [&](int tile, int kb, Buf& b) {
+            const int kvalid = (kb == nkb - 1) ? last_k : KBLK;      // channels of this block the MMA will read
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int k = k0 + u;
-                        float x = 0.f;
-                        if (valid && k < K) {
-                            const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
-                            const int c = k - (sg == 0 ? 0 : S.cend[sg - 1]);
-                            x = __ldg(S.src[sg] + (long)c * S.plane + p);
-                            if (sg == S.gate_seg) {
-                                const int gc = S.gate_ch0 + c;
-                                const float g = __ldg(S.gate_pre + (long)gc * S.plane + p);
-                                x *= sigmoid_acc(fmaf(g, __ldg(S.gate_scale + gc), __ldg(S.gate_shift + gc)));
+            for (int c = 0; c < 2; ++c) {
+                const int idx = pt + c * NPROD;
+                const int ch = idx >> 4, px = (idx & 15) * 8;
+                const int k = kb * KBLK + ch;
+                const long p = (long)tile * TILE_M + px;
+                b.gch[c] = -1;
+                if (ch < kvalid && k < K && p < N) {
+                    const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
+                    const int cc = k - (sg == 0 ? 0 : S.cend[sg - 1]);
+                    const float* src = S.src[sg] + (long)cc * S.plane + p;
+                    const bool gated = GATED && sg == S.gate_seg;
+                    const float* gp = nullptr;
+                    if (gated) { b.gch[c] = S.gate_ch0 + cc; gp = S.gate_pre + (long)b.gch[c] * S.plane + p; }
+                    if (S.vec && p + 8 <= N) {
+                        const float4 lo = __ldg(reinterpret_cast<const float4*>(src));
+                        const float4 hi = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        b.v[c][0] = lo.x; b.v[c][1] = lo.y; b.v[c][2] = lo.z; b.v[c][3] = lo.w;
+                        b.v[c][4] = hi.x; b.v[c][5] = hi.y; b.v[c][6] = hi.z; b.v[c][7] = hi.w;
+                        if constexpr (GATED) {
+                            if (gated) {
+                                const float4 glo = __ldg(reinterpret_cast<const float4*>(gp));
+                                const float4 ghi = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+                                b.g[c][0] = glo.x; b.g[c][1] = glo.y; b.g[c][2] = glo.z; b.g[c][3] = glo.w;
+                                b.g[c][4] = ghi.x; b.g[c][5] = ghi.y; b.g[c][6] = ghi.z; b.g[c][7] = ghi.w;
                             }
                         }
-                        v[u] = x;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool in = p + u < N;
+                            b.v[c][u] = in ? __ldg(src + u) : 0.f;
+                            if constexpr (GATED) { if (gated) b.g[c][u] = in ? __ldg(gp + u) : 0.f; }
+                        }
                     }
-                    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    *reinterpret_cast<uint4*>(row + ((j ^ (pr & 7)) << 4)) = pk;
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) b.v[c][u] = 0.f;
                 }
-                fence_proxy_async();                         // generic-proxy stores -> visible to tcgen05.mma
-                mbar_arrive(full0 + 8 * stage);
-                TC_DBG(1 + (warp - 4), (unsigned)(tile * 100 + kb + 1));
-                if (++stage == P.nstage) { stage = 0; phase ^= 1; }
             }
+        };
+        auto commit = [&](int kb, int stage, Buf& b) {
+            uint8_t* st = sm + a_off + stage * STAGE_BYTES;
+            const int kvalid = (kb == nkb - 1) ? last_k : KBLK;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int idx = pt + c * NPROD;
+                const int ch = idx >> 4, px8 = idx & 15;
+                if (ch < kvalid) {
+                    if constexpr (GATED) {
+                        if (b.gch[c] >= 0) {
+                            const float sc = __ldg(S.gate_scale + b.gch[c]), sh = __ldg(S.gate_shift + b.gch[c]);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) b.v[c][u] *= sigmoid_fast(fmaf(b.g[c][u], sc, sh));
+                        }
+                    }
+                    uint4 pk = make_uint4(pack_bf16(b.v[c][0], b.v[c][1]), pack_bf16(b.v[c][2], b.v[c][3]),
+                                          pack_bf16(b.v[c][4], b.v[c][5]), pack_bf16(b.v[c][6], b.v[c][7]));
+                    const int kk = ch & 7;
+                    *reinterpret_cast<uint4*>(st + (px8 >> 3) * 8192 + (ch >> 3) * 1024 + kk * 128 + (((px8 & 7) ^ kk) << 4)) = pk;
+                }
+            }
+            fence_proxy_async();                             // generic-proxy stores -> visible to tcgen05.mma
+            mbar_arrive(full0 + 8 * stage);
+            if (warp == NEPI / 32 && kb == nkb - 1) { TC_TRACE(1, trace_i); ++trace_i; }
+        };
+
+        int stage = 0; uint32_t phase = 0;
+        int tile = blockIdx.x, kb = 0;
+        Buf b0, b1;
+        bool have = tile < ntiles;
+        if (have) issue(tile, kb, b0);
+        while (have) {
+            // ---- even unit lives in b0; prefetch the next into b1
+            int ntile = tile, nkbi = kb + 1;
+            if (nkbi == nkb) { nkbi = 0; ntile += gridDim.x; }
+            bool nhave = ntile < ntiles;
+            if (nhave) issue(ntile, nkbi, b1);
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            commit(kb, stage, b0);
+            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
+            if (!nhave) break;
+            // ---- odd unit lives in b1; prefetch the next into b0
+            tile = ntile; kb = nkbi;
+            ntile = tile; nkbi = kb + 1;
+            if (nkbi == nkb) { nkbi = 0; ntile += gridDim.x; }
+            nhave = ntile < ntiles;
+            if (nhave) issue(ntile, nkbi, b0);
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            commit(kb, stage, b1);
+            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
+            tile = ntile; kb = nkbi; have = nhave;
         }
-    } else if (warp == 8) {
+    } else if (warp == MMA_WARP) {
         // =========================================================================== MMA issuer
         // every lane follows the pipeline (waits), lane 0 alone issues tcgen05.mma / tcgen05.commit
         const uint32_t idesc = instr_desc_bf16(NOUT);
@@ -244,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                     const uint32_t b_addr = base + w_off + kb * wblk_bytes;
                     const int nmma = ((kb == nkb - 1) ? last_k : KBLK) >> 4;
                     for (int j = 0; j < nmma; ++j)
-                        umma_f16(d_tmem, smem_desc_sw128(a_addr + j * 32), smem_desc_sw128(b_addr + j * 32), idesc,
+                        umma_f16(d_tmem, smem_desc_mn_sw128(a_addr + j * 2048), smem_desc_sw128(b_addr + j * 32), idesc,
                                  (kb | j) ? 1u : 0u);
                     umma_commit(empty0 + 8 * stage);         // frees the ring slot when these MMAs retire
                 }
@@ -254,49 +341,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             }
             if (lane == 0) umma_commit(tfull0 + 8 * as);     // accumulator complete -> epilogue
             __syncwarp();
+            TC_TRACE(2, (tile - (int)blockIdx.x) / (int)gridDim.x);
             as ^= 1; if (as == 0) aphase ^= 1;
         }
     } else {
-        // =========================================================================== epilogue (warps 0-3)
+        // =========================================================================== epilogue (warps 0-7)
+        // warp w: TMEM lanes 32*(w&3).. (pixels), 32-column groups g = (w>>2), (w>>2)+2, ... (output channels)
         int as = 0; uint32_t aphase = 0;
         const int ng = NOUT >> 5;
+        const int lq = warp & 3, ghalf = warp >> 2;
+        const int row = lq * 32 + lane;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long p = (long)tile * TILE_M + tid;        // TMEM lane = tid (warp w owns lanes 32w..32w+31)
+            const long p = (long)tile * TILE_M + row;
             const bool valid = p < N;
+            const float vmask = valid ? 1.f : 0.f;
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * acc_stride);
+            if (warp == 0) TC_TRACE(3, (tile - (int)blockIdx.x) / (int)gridDim.x);
+            const uint32_t t_addr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(as * acc_stride);
 #pragma unroll
-            for (int g = 0; g < MAXG; ++g) {
+            for (int gi = 0; gi < MAXG / 2; ++gi) {
+                const int g = ghalf + 2 * gi;
                 if (g < ng) {
                     float v[32];
                     tmem_ld32(t_addr + g * 32, v);
-                    float s = 0.f, ss = 0.f;
-                    float* o = P.out + (long)(g * 32) * P.out_plane + p;
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                    float* o = P.out + (long)(g * 32) * P.out_plane + (valid ? p : 0);
+                    const float* bs = sbias + g * 32;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float y = v[i] + sbias[g * 32 + i];
-                        if (valid) { o[(long)i * P.out_plane] = y; s += y; ss = fmaf(y, y, ss); }
+                    for (int i = 0; i < 32; i += 2) {
+                        const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
+                        if (valid) { o[0] = y0; o[P.out_plane] = y1; }
+                        o += 2 * P.out_plane;
+                        s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
                     }
-                    st_s[g] += s; st_ss[g] += ss;
+                    st_s[gi] += (s0 + s1) * vmask; st_ss[gi] += (q0 + q1) * vmask;
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * as);
-            TC_DBG(6 + warp, (unsigned)(tile + 1));
+            if (warp == 0) TC_TRACE(4, (tile - (int)blockIdx.x) / (int)gridDim.x);
             as ^= 1; if (as == 0) aphase ^= 1;
         }
-        // per-CTA GroupNorm partials (fixed order: lanes -> warps -> CTA)
+        // per-CTA GroupNorm partials (fixed order: lanes -> lane quarters -> CTA)
 #pragma unroll
-        for (int g = 0; g < MAXG; ++g) {
+        for (int gi = 0; gi < MAXG / 2; ++gi) {
+            const int g = ghalf + 2 * gi;
             if (g < ng) {
-                float a = warp_sum(st_s[g]), b = warp_sum(st_ss[g]);
-                if (lane == 0) { red[0][warp][g] = a; red[1][warp][g] = b; }
+                float a = warp_sum(st_s[gi]), b = warp_sum(st_ss[gi]);
+                if (lane == 0) { red[0][lq][g] = a; red[1][lq][g] = b; }
             }
         }
     }
     tc_fence_before();
-    TC_DBG(10 + (warp > 4 ? 4 : warp), 0xD0u);
+    if (tid == 0) TC_TRACE(5, 0);
     __syncthreads();
     if (tid < (NOUT >> 5)) {
         float a = 0.f, b = 0.f;
@@ -304,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         for (int w = 0; w < 4; ++w) { a += red[0][w][tid]; b += red[1][w][tid]; }
         P.sink.partial[(size_t)tid * P.sink.stride + blockIdx.x] = make_float2(a, b);
     }
-    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
+    if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
     stats_finalize_last_cta(P.sink, gridDim.x, gridDim.x, &P.aff);
 }
 

@@ -45,6 +45,8 @@ struct Arena {
 
 // ---- device math -------------------------------------------------------------------------------
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// reduced-precision modes only: ex2.approx + rcp.approx (about 2 ulp), the result is rounded to bf16 anyway
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float lrelu(float x, float slope) { return x >= 0.f ? x : x * slope; }
 __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
 
