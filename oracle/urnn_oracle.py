@@ -64,12 +64,14 @@ def conv2d_same(x, w, b=None, quant=None):
     return y
 
 
-def group_norm(x, num_groups, gamma, beta, eps=GN_EPS):
-    """nn.GroupNorm over (C/G channels x H x W), biased variance.  ConvRNN.py:97,103."""
+def group_norm(x, num_groups, gamma, beta, eps=GN_EPS, stats_from=None):
+    """nn.GroupNorm over (C/G channels x H x W), biased variance.  ConvRNN.py:97,103.
+    stats_from (bf16 storage model only): take mean/variance from this array instead of x."""
     c, h, w = x.shape
     g = x.reshape(num_groups, -1)
-    mean = g.mean(axis=1, keepdims=True)
-    var = ((g - mean) ** 2).mean(axis=1, keepdims=True)
+    gs = g if stats_from is None else stats_from.reshape(num_groups, -1)
+    mean = gs.mean(axis=1, keepdims=True)
+    var = ((gs - mean) ** 2).mean(axis=1, keepdims=True)
     y = ((g - mean) / np.sqrt(var + x.dtype.type(eps))).reshape(c, h, w)
     return y * gamma[:, None, None] + beta[:, None, None]
 
@@ -129,12 +131,17 @@ def cgru_cell_step(p, prefix, x, hidden, module, num_features, quant=None):
     g1w, g1b = p[prefix + "conv1.1.weight"], p[prefix + "conv1.1.bias"]
     w2, b2 = p[prefix + "conv2.0.weight"], p[prefix + "conv2.0.bias"]
     g2w, g2b = p[prefix + "conv2.1.weight"], p[prefix + "conv2.1.bias"]
+    x_was_none = x is None
     if x is None:
         cin = w1.shape[1] - hidden.shape[0]
         x = np.zeros((cin,) + hidden.shape[1:], dtype=hidden.dtype)
     combined_1 = np.concatenate([x, hidden], axis=0)                 # ConvRNN.py:153
     gates_pre = conv2d_same(combined_1, w1, b1, quant)
-    gates = group_norm(gates_pre, (2 * F) // 32, g1w, g1b)           # ConvRNN.py:97
+    if quant == "bf16":
+        # storage model of URNN_MATH_BF16: the pre-GN maps are kept as bf16, statistics come from the fp32 values
+        gates = group_norm(round_bf16(gates_pre), (2 * F) // 32, g1w, g1b, stats_from=gates_pre)
+    else:
+        gates = group_norm(gates_pre, (2 * F) // 32, g1w, g1b)       # ConvRNN.py:97
     z = sigmoid(gates[:F])                                           # ConvRNN.py:160-162
     r = sigmoid(gates[F:])
     if module == "encoder":
@@ -144,8 +151,18 @@ def cgru_cell_step(p, prefix, x, hidden, module, num_features, quant=None):
         e, d = hidden[:F], hidden[F:]                                # ConvRNN.py:172
         combined_2 = np.concatenate([x, e, r * d], axis=0)           # ConvRNN.py:173
         prev = d
-    cand_pre = conv2d_same(combined_2, w2, b2, quant)
-    cand = np.tanh(group_norm(cand_pre, F // 32, g2w, g2b))          # ConvRNN.py:103,180
+    kxe = combined_2.shape[0] - F                                    # channels not touched by the reset gate
+    kskip = x.shape[0] if x_was_none else 0                          # zero-input columns are skipped by the kernel
+    if quant == "bf16" and 3 * F <= 256 and kxe - kskip > 0:
+        # the r-independent part of the candidate is produced by the first sweep and stored as bf16
+        part = round_bf16(conv2d_same(combined_2[:kxe], w2[:, :kxe], None, quant))
+        cand_pre = part + conv2d_same(combined_2[kxe:], w2[:, kxe:], b2, quant)
+    else:
+        cand_pre = conv2d_same(combined_2, w2, b2, quant)
+    if quant == "bf16":
+        cand = np.tanh(group_norm(round_bf16(cand_pre), F // 32, g2w, g2b, stats_from=cand_pre))
+    else:
+        cand = np.tanh(group_norm(cand_pre, F // 32, g2w, g2b))      # ConvRNN.py:103,180
     h_next = (1 - z) * prev + z * cand                               # ConvRNN.py:185,189
     return h_next.astype(hidden.dtype), gates_pre, cand_pre
 

@@ -1,10 +1,10 @@
 """URNN_MATH_BF16 (tcgen05) mode on the GPU.
 
 Two checks per case:
-  * against the oracle with the gate-contraction operands rounded to bf16 (oracle quant="bf16"): the kernel
-    must implement exactly "round operands to bf16, multiply exactly, accumulate in fp32", so the mean error
-    is at fp32 noise level (<= 1e-6) and the max is bounded by rare one-ulp bf16 rounding flips of r*h
-    (atol 2e-3);
+  * against the oracle's model of the mode (oracle quant="bf16": GEMM operands rounded to bf16, products exact,
+    fp32 accumulation, pre-GroupNorm maps stored as bf16, statistics from the fp32 values): the kernel must
+    implement exactly that dataflow, so the only differences are rare one-ulp bf16 rounding flips where the
+    fp32 and fp64 pre-rounding values straddle a rounding boundary: mean |err| <= 5e-6, max |err| <= 8e-3;
   * against the exact fp32-semantics oracle: the stated bf16-mode tolerance, max |err| <= 3e-2 and
     mean |err| <= 2e-3 per cell step on O(1) states (SURVEY.md 8d config 3 budget: max |dstate| <= 1e-1).
 """
@@ -35,8 +35,8 @@ def test_bf16_cell_vs_quantised_oracle(H, W, cin, F, module, with_x):
     hn = hid.numpy()[0].astype(np.float64)
     refq = O.cgru_cell_forward(w, "", xn, hn, module, F, 1, quant="bf16")[0]
     ref = O.cgru_cell_forward(w, "", xn, hn, module, F, 1)[0]
-    assert np.abs(out - refq).max() <= 2e-3
-    assert np.abs(out - refq).mean() <= 1e-6
+    assert np.abs(out - refq).max() <= 8e-3
+    assert np.abs(out - refq).mean() <= 5e-6
     assert np.abs(out - ref).max() <= 3e-2
     assert np.abs(out - ref).mean() <= 2e-3
 

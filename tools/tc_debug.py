@@ -4,7 +4,7 @@ os.environ["CUDA_MODULE_LOADING"] = "EAGER"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "u-rnn_b200")]
 import numpy as np, torch, faulthandler
-faulthandler.dump_traceback_later(40, exit=True)
+faulthandler.dump_traceback_later(200, exit=True)
 from oracle import urnn_oracle as O
 from src.lib.model.networks.ConvRNN import CGRU_cell
 
@@ -32,5 +32,4 @@ if __name__ == "__main__":
     run(32, 32, 96, 96, "decoder", with_x=False)
     run(125, 125, 96, 96, "decoder")
     run(250, 250, 64, 96, "encoder")
-    run(500, 500, 96, 64, "decoder")
     run(9, 11, 5, 32, "encoder")

@@ -1,10 +1,16 @@
-// cgru_tc.cu -- URNN_MATH_BF16 path of the (Skip-)ConvGRU cell: the two gate contractions run on tcgen05
-// (tc_pixgemm.cuh), GroupNorm statistics are fused into their epilogues, the gate/blend sweep is shared with
-// the fp32 path.  k = 1 only (the production configuration); other filter sizes use the fp32 path.
+// cgru_tc.cu -- URNN_MATH_BF16 path of the (Skip-)ConvGRU cell (k = 1; other filter sizes use the fp32 path).
+//
+// Three sweeps separated by the two GroupNorm statistics (ConvRNN.py:94-104 make a one-pass cell impossible):
+//   A  tcgen05 GEMM  [x|e|h] -> G = W1.u + b1 (2F ch, GN-1 statistics fused)  and, when 3F <= 256,
+//                               Pc = W2[:, x|e].[x|e] (F ch): the part of the candidate that does not depend on r
+//   B  tcgen05 GEMM  r = sigmoid(GN1(G)[F:]) applied to h on the way into shared memory;
+//                    C = Pc + W2[:, h].(r*h) + b2   (K = F only)          [3F <= 256]
+//                    C = W2.[x|e|r*h] + b2          (K = Cx+Ch)           [otherwise]      (GN-2 statistics fused)
+//   C  elementwise   z = sigmoid(GN1(G)[:F]); h' = (1-z) h + z tanh(GN2(C))
+// G, Pc, C live in the workspace as bf16 maps (they are re-read once each); states stay fp32.
+#include <stdlib.h>
 #include "tc_pixgemm.cuh"
 #include "urnn_internal.h"
-#include <stdlib.h>
-#define TRACE(...) do { if (getenv("URNN_TRACE")) { fprintf(stderr, __VA_ARGS__); fflush(stderr); } } while (0)
 
 namespace urnn {
 
@@ -23,7 +29,6 @@ static int tc_launch(tc::GemmParams& P, cudaStream_t st) {
         else       URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
         g_attr_set[gated] = true;
     }
-    TRACE("tc_launch: NOUT=%d K=%d N=%d sms=%d\n", P.NOUT, P.K, P.N, g_num_sms);
     int nstage = 0;
     size_t smem = tc::gemm_smem_bytes(P.NOUT, P.K, &nstage);
     if (smem == 0) { set_error("tc gemm: weights %dx%d do not fit in shared memory", P.NOUT, P.K); return URNN_E_UNSUPPORTED; }
@@ -31,14 +36,63 @@ static int tc_launch(tc::GemmParams& P, cudaStream_t st) {
     int cols = 32;
     while (cols < 2 * P.NOUT) cols <<= 1;
     P.tmem_cols = cols;
+    P.dbg = nullptr;
     int ntiles = (P.N + tc::TILE_M - 1) / tc::TILE_M;
     int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
-    TRACE("tc_launch: grid=%d smem=%zu nstage=%d cols=%d\n", grid, smem, nstage, cols);
     if (gated) tc::gemm_gn_kernel<true><<<grid, tc::NTHREADS, smem, st>>>(P);
     else       tc::gemm_gn_kernel<false><<<grid, tc::NTHREADS, smem, st>>>(P);
     URNN_LAUNCH_CHECK();
-    TRACE("tc_launch: launched\n");
     return URNN_OK;
+}
+
+// h' = (1-z)*h + z*tanh(GN2(C)),  z = sigmoid(GN1(G)[:F]); G and C are bf16 maps, flat over (channel, pixel)
+__global__ void __launch_bounds__(256)
+cgru_blend_bf16_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ C,
+                       const float* __restrict__ h, const float* __restrict__ sc1, const float* __restrict__ sh1,
+                       const float* __restrict__ sc2, const float* __restrict__ sh2, float* __restrict__ h_out,
+                       long N, long nquad) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nquad) return;
+    const uint2 gw = __ldg(reinterpret_cast<const uint2*>(G) + idx);
+    const uint2 cw = __ldg(reinterpret_cast<const uint2*>(C) + idx);
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(h) + idx);
+    float gv[4], cv[4];
+    tc::unpack_bf16x2(gw.x, gv[0], gv[1]); tc::unpack_bf16x2(gw.y, gv[2], gv[3]);
+    tc::unpack_bf16x2(cw.x, cv[0], cv[1]); tc::unpack_bf16x2(cw.y, cv[2], cv[3]);
+    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+    float o[4];
+    const int c0 = (int)((idx * 4) / N), c3 = (int)((idx * 4 + 3) / N);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int c = (c0 == c3) ? c0 : (int)((idx * 4 + u) / N);
+        const float a1 = __ldg(sc1 + c), b1 = __ldg(sh1 + c), a2 = __ldg(sc2 + c), b2 = __ldg(sh2 + c);
+        const float z = sigmoid_acc(fmaf(gv[u], a1, b1)), t = tanhf(fmaf(cv[u], a2, b2));
+        o[u] = (1.f - z) * hh[u] + z * t;
+    }
+    reinterpret_cast<float4*>(h_out)[idx] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+struct CellWsBf16 {
+    unsigned* counter; double2 *total1, *total2; float *scale1, *shift1, *scale2, *shift2;
+    float2 *partial1, *partial2; __nv_bfloat16 *GP, *C; int gx;
+};
+
+static size_t cell_ws_bf16(const urnn_cell_desc* d, void* ws, size_t ws_bytes, CellWsBf16* out) {
+    const long N = (long)d->H * d->W;
+    const int F = d->F, gx = (int)((N + tc::TILE_M - 1) / tc::TILE_M);
+    Arena a(ws, ws_bytes);
+    CellWsBf16 w;
+    w.gx = gx;
+    w.counter = a.take<unsigned>(64);
+    w.total1 = a.take<double2>(2 * F / 32); w.total2 = a.take<double2>(F / 32);
+    w.scale1 = a.take<float>(2 * F); w.shift1 = a.take<float>(2 * F);
+    w.scale2 = a.take<float>(F);     w.shift2 = a.take<float>(F);
+    w.partial1 = a.take<float2>((size_t)(2 * F / 32) * gx);
+    w.partial2 = a.take<float2>((size_t)(F / 32) * gx);
+    w.GP = a.take<__nv_bfloat16>((size_t)3 * F * N);
+    w.C = a.take<__nv_bfloat16>((size_t)F * N);
+    if (out) *out = w;
+    return align_up(a.off, 256);
 }
 
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
@@ -50,42 +104,60 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     const int Ktot = d->Cx + Ch;
     const int Cx_eff = x ? d->Cx : 0;
     const int Keff = Cx_eff + Ch;
+    const int Kxe = Keff - F;                           // channels that do not pass through the reset gate
     const long aoff = x ? 0 : d->Cx;                    // skip the zero-input weight columns (ConvRNN.py:143-146)
     if (2 * F > 256) { set_error("cgru_fwd(bf16): num_features=%d > 128 not supported by the tcgen05 tile", F); return URNN_E_UNSUPPORTED; }
-    CellWsView w;
-    size_t need = cell_ws_view(d, ws, ws_bytes, &w);
+    const bool split = (3 * F <= 256) && Kxe > 0;       // compute the r-independent part of the candidate in sweep A
+    CellWsBf16 w;
+    size_t need = cell_ws_bf16(d, ws, ws_bytes, &w);
     if (need > ws_bytes) { set_error("cgru_fwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
-    TRACE("cgru_fwd_bf16: F=%d N=%ld Keff=%d\n", F, N, Keff);
     URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
-    TRACE("cgru_fwd_bf16: memset ok\n");
 
     tc::GemmParams P;
-    P.dbg = nullptr;
     // segments [x | e | h]; missing ones get zero width
     int n = 0; const float* srcs[3] = {h, h, h}; int cnt[3] = {0, 0, 0};
     if (x) { srcs[n] = x; cnt[n] = d->Cx; ++n; }
     if (d->variant == URNN_CELL_DECODER) { srcs[n] = e; cnt[n] = F; ++n; }
     srcs[n] = h; cnt[n] = F; const int hseg = n; ++n;
     int acc = 0;
-    for (int i = 0; i < 3; ++i) { P.seg.src[i] = srcs[i]; acc += cnt[i]; P.seg.cend[i] = acc; }
+    for (int i = 0; i < 3; ++i) { P.seg.src[i] = srcs[i]; P.seg.kind[i] = 0; acc += cnt[i]; P.seg.cend[i] = acc; }
     P.seg.plane = N;
-    P.seg.vec = (N % 4 == 0) && ((((uintptr_t)x | (uintptr_t)e | (uintptr_t)h | (uintptr_t)w.G) & 15) == 0);
     P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
-    P.N = (int)N; P.K = Keff; P.w_ld = Ktot;
+    P.N = (int)N; P.K = Keff; P.out_plane = N; P.addend = nullptr;
 
-    // pass A: G = W1 [x|e|h] + b1, GroupNorm-1 statistics
-    P.W = p->w1 + aoff; P.bias = p->b1; P.NOUT = 2 * F; P.out = w.G; P.out_plane = N;
+    // ---- sweep A
+    P.W = p->w1 + aoff; P.w_ld = Ktot; P.nrow1 = 2 * F;
+    P.W2 = p->w2 + aoff; P.w2_ld = Ktot; P.k2 = Kxe;
+    P.bias = p->b1; P.nbias = 2 * F;
+    P.NOUT = split ? 3 * F : 2 * F;
+    P.out = w.GP; P.nstat = 2 * F / 32;
     P.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx};
     P.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, 32.0 * (double)N, d->eps};
     URNN_TRY(tc_launch(P, st));
-    // pass B: C = W2 [x|e|r*h] + b2 with r = sigmoid(GN1(G)[F:]), GroupNorm-2 statistics
-    P.seg.gate_seg = hseg; P.seg.gate_ch0 = F; P.seg.gate_pre = w.G; P.seg.gate_scale = w.scale1; P.seg.gate_shift = w.shift1;
-    P.W = p->w2 + aoff; P.bias = p->b2; P.NOUT = F; P.out = w.C;
+
+    // ---- sweep B
+    P.seg.gate_ch0 = F; P.seg.gate_pre = w.GP; P.seg.gate_scale = w.scale1; P.seg.gate_shift = w.shift1;
+    if (split) {
+        P.seg.src[0] = h; P.seg.kind[0] = 0; P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = F;
+        P.seg.gate_seg = 0;
+        P.K = F; P.W = p->w2 + aoff + Kxe;
+        P.addend = w.GP + (size_t)2 * F * N;
+    } else {
+        P.seg.gate_seg = hseg;
+        P.W = p->w2 + aoff;
+    }
+    P.w_ld = Ktot; P.nrow1 = F; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0;
+    P.bias = p->b2; P.nbias = F; P.NOUT = F; P.out = w.C; P.nstat = F / 32;
     P.sink = StatSink{w.partial2, w.total2, w.counter + 1, F / 32, w.gx};
     P.aff = AffineOut{w.scale2, w.shift2, p->gn2_w, p->gn2_b, F, 32, 32.0 * (double)N, d->eps};
     URNN_TRY(tc_launch(P, st));
-    // pass C: gates + blend (shared with the fp32 path)
-    return cgru_blend_launch(w, h, h_out, F, N, st);
+
+    // ---- sweep C
+    const long nquad = (long)F * N / 4;
+    cgru_blend_bf16_kernel<<<(unsigned)((nquad + 255) / 256), 256, 0, st>>>(w.GP, w.C, h, w.scale1, w.shift1, w.scale2,
+                                                                            w.shift2, h_out, N, nquad);
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
 }
 
 }  // namespace urnn

@@ -1,18 +1,23 @@
 // tc_pixgemm.cuh -- tcgen05 "pixel GEMM" for sm_100a:  D[128 pixels x NOUT] = X^T[128 x K] * W^T[K x NOUT]
-// with bf16 operands (rounded on the fly from fp32 NCHW maps) and fp32 accumulation in tensor memory.
+// with bf16 operands (rounded on the fly from the fp32 / bf16 NCHW maps) and fp32 accumulation in tensor memory.
 //
 // One persistent CTA per SM, 25 warps, warp-specialised:
-//   warps 0-7  epilogue : tcgen05.ld the accumulator (TMEM lane = pixel, column = output channel), fused epilogue
-//   warps 8-23 producers: 4 threads per pixel, software-pipelined two K blocks deep; coalesced fp32 loads of the (virtually concatenated, optionally
-//                         reset-gated) input channels -> bf16 -> 128B-swizzled K-major shared-memory tile
-//   warp  24   MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=NOUT, K=16 per instruction
+//   warps 0-7   epilogue : tcgen05.ld the accumulator (TMEM lane = pixel, column = output channel); fused epilogue
+//                          (bias, optional addend map, GroupNorm statistics, bf16 NCHW store)
+//   warps 8-23  producers: build the A tile.  It is stored MN-major (pixel-contiguous) exactly like the NCHW source,
+//                          so a thread moves 8 consecutive pixels of one channel (two 16-byte global loads -> 8 bf16
+//                          -> one 16-byte shared store) and a half-warp covers the 512 contiguous bytes a channel
+//                          contributes to the tile.  The channel axis is a virtual concatenation of up to three maps;
+//                          one segment can be multiplied by the reset gate sigmoid(GN(G_r)) on the way in.
+//   warp  24    MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=NOUT, K=16 per instruction
 // Pipelines: K-block ring in shared memory (full/empty mbarriers, producer -> MMA) and a double-buffered
 // accumulator in TMEM (tmem_full/tmem_empty mbarriers, MMA -> epilogue), so loads, MMAs and epilogues of
-// successive 128-pixel tiles overlap.  Weights are converted once per CTA and stay resident in shared memory.
+// successive 128-pixel tiles overlap; producers additionally keep the loads of the next ring slot in flight
+// while converting the current one.  Weights are converted once per CTA and stay resident in shared memory.
 //
-// The activations pass through registers because they must be rounded fp32 -> bf16 (and, for the candidate
-// GEMM, multiplied by the reset gate) before the tensor core sees them; TMA cannot do either, so the
-// producer is SIMT and publishes its stores to the async proxy with fence.proxy.async.
+// Why no TMA for the activations: they must be rounded fp32 -> bf16 (and, for the candidate GEMM, multiplied by
+// the reset gate) before the tensor core sees them.  The producer is therefore SIMT and publishes its shared
+// stores to the async proxy with fence.proxy.async.
 #pragma once
 #include <cuda_bf16.h>
 #include "urnn_common.cuh"
@@ -21,14 +26,14 @@ namespace urnn {
 namespace tc {
 
 constexpr int TILE_M = 128;           // pixels per tile (TMEM lanes)
-constexpr int KBLK = 64;              // bf16 elements per 128-byte swizzle row
-constexpr int STAGE_BYTES = TILE_M * 128;
-constexpr int NPROD = 512;            // producer threads: 4 per tile row (each takes 2 of a K block's 8 chunks)
-constexpr int NEPI = 256;             // epilogue threads: warp w owns TMEM lanes 32*(w%4).. and column half w/4
+constexpr int KBLK = 64;              // channels per ring slot
+constexpr int STAGE_BYTES = TILE_M * KBLK * 2;
+constexpr int NPROD = 512;            // producer threads
+constexpr int NEPI = 256;             // epilogue threads: warp w owns TMEM lanes 32*(w%4).. and column groups w/4, w/4+2, ..
 constexpr int NTHREADS = NEPI + NPROD + 32;
 constexpr int MMA_WARP = (NEPI + NPROD) / 32;
-constexpr int MAXG = 8;
-constexpr size_t SMEM_CAP = 229376;  // dynamic shared memory budget (227 KB opt-in limit minus static use)               // NOUT <= 256 -> at most 8 GroupNorm groups per tile row
+constexpr int MAXG = 8;               // NOUT <= 256 -> at most 8 groups of 32 output channels
+constexpr size_t SMEM_CAP = 229376;   // dynamic shared memory budget (227 KB opt-in limit minus static use)
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,7 +95,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart)
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart): weights
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address
@@ -120,28 +125,67 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ void unpack_bf16x2(uint32_t w, float& a, float& b) {
+    a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xFFFF0000u);
+}
+
+// 8 consecutive elements starting at element offset `off` of an fp32 (kind 0) or bf16 (kind 1) map; `nvalid` of them
+// are inside the map.  The widest aligned vector access available is used.
+__device__ __forceinline__ void load8(const void* base, int kind, long off, int nvalid, float (&v)[8]) {
+    if (kind == 0) {
+        const float* s = reinterpret_cast<const float*>(base) + off;
+        if (nvalid == 8 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+            const float4 lo = __ldg(reinterpret_cast<const float4*>(s));
+            const float4 hi = __ldg(reinterpret_cast<const float4*>(s) + 1);
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (u < nvalid) ? __ldg(s + u) : 0.f;
+        }
+    } else {
+        const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(base) + off;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+        if (nvalid == 8 && (a & 15) == 0) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(s));
+            unpack_bf16x2(w.x, v[0], v[1]); unpack_bf16x2(w.y, v[2], v[3]);
+            unpack_bf16x2(w.z, v[4], v[5]); unpack_bf16x2(w.w, v[6], v[7]);
+        } else if (nvalid == 8 && (a & 7) == 0) {
+            const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(s));
+            const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(s) + 1);
+            unpack_bf16x2(w0.x, v[0], v[1]); unpack_bf16x2(w0.y, v[2], v[3]);
+            unpack_bf16x2(w1.x, v[4], v[5]); unpack_bf16x2(w1.y, v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (u < nvalid) ? __bfloat162float(s[u]) : 0.f;
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------- parameters
-// Virtual channel concatenation of up to three fp32 NCHW sources; the segment `gate_seg` (or none: -1) is
-// multiplied by sigmoid(gate_pre[gate_ch0 + c] * gate_scale[..] + gate_shift[..]) (the reset gate).
+// Virtual channel concatenation of up to three NCHW maps (fp32: kind 0, bf16: kind 1).  The segment `gate_seg`
+// (or none: -1) is multiplied by sigmoid(gate_pre[gate_ch0 + c] * gate_scale[..] + gate_shift[..]) (reset gate;
+// gate_pre is a bf16 map).
 struct Segs {
-    const float* src[3]; int cend[3];
+    const void* src[3]; int cend[3]; int kind[3];
     long plane;
     int gate_seg; int gate_ch0;
-    bool vec;                      // plane % 4 == 0 and every source 16-byte aligned: float4 loads
-    const float* gate_pre; const float* gate_scale; const float* gate_shift;
+    const __nv_bfloat16* gate_pre; const float* gate_scale; const float* gate_shift;
 };
 
 struct GemmParams {
     Segs seg;
-    const float* W; long w_ld;        // weights W[n * w_ld + k], n < NOUT, k < K (fp32, converted per CTA)
-    const float* bias;                // [NOUT]
-    int NOUT, K, N;                   // output channels (multiple of 32, <= 256), reduction size, pixels
-    float* out; long out_plane;       // fp32 NCHW destination of (acc + bias)
-    StatSink sink; AffineOut aff;     // GroupNorm statistics of the destination (32 channels per set)
-    int nstage;                       // K-block ring depth
-    int tmem_cols;                    // power of two >= 2 * NOUT
-    volatile unsigned* dbg;           // optional host-mapped progress words (bring-up only), else nullptr
+    // weights: row n < nrow1 is W[n*w_ld + k]; row n >= nrow1 is W2[(n-nrow1)*w2_ld + k] for k < k2 and 0 beyond
+    const float* W; long w_ld; int nrow1;
+    const float* W2; long w2_ld; int k2;
+    const float* bias; int nbias;            // bias[n] for n < nbias, zero beyond
+    int NOUT, K, N;                          // output channels (multiple of 32, <= 256), reduction size, pixels
+    __nv_bfloat16* out; long out_plane;      // bf16 NCHW destination of (acc + bias [+ addend])
+    const __nv_bfloat16* addend;             // optional bf16 map [NOUT][plane] added before store / statistics
+    int nstat;                               // leading 32-channel groups whose (sum, sumsq) go to `sink`
+    StatSink sink; AffineOut aff;
+    int nstage;                              // K-block ring depth
+    int tmem_cols;                           // power of two >= 2 * NOUT
+    volatile unsigned* dbg;                  // optional host-mapped progress / trace words (bring-up only)
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
@@ -156,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const int NOUT = P.NOUT, K = P.K, N = P.N;
     const int Kp = (K + 15) & ~15;                          // padded to the MMA K
     const int nkb = (Kp + KBLK - 1) / KBLK;                 // K blocks per tile
-    const int last_k = Kp - (nkb - 1) * KBLK;               // valid (padded) columns in the last block
+    const int last_k = Kp - (nkb - 1) * KBLK;               // valid (padded) channels in the last block
     const int wblk_bytes = NOUT * 128;
     const uint32_t w_off = 0;
     const uint32_t a_off = w_off + (uint32_t)nkb * wblk_bytes;
@@ -176,15 +220,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
-    for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = __ldg(P.bias + i);
+    for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = (i < P.nbias) ? __ldg(P.bias + i) : 0.f;
     {
         const int chunks_per_row = nkb * 8;                 // 16-byte chunks (8 bf16) per weight row
         for (int idx = tid; idx < NOUT * chunks_per_row; idx += NTHREADS) {
-            int n = idx / chunks_per_row, ch = idx % chunks_per_row;
-            int kb = ch >> 3, j = ch & 7, k0 = kb * KBLK + j * 8;
+            const int n = idx / chunks_per_row, ch = idx % chunks_per_row;
+            const int kb = ch >> 3, j = ch & 7, k0 = kb * KBLK + j * 8;
+            const bool second = n >= P.nrow1;
+            const float* wrow = second ? (P.W2 + (long)(n - P.nrow1) * P.w2_ld) : (P.W + (long)n * P.w_ld);
+            const int klim = second ? (P.k2 < K ? P.k2 : K) : K;
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < K) ? __ldg(P.W + (long)n * P.w_ld + k0 + u) : 0.f;
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim) ? __ldg(wrow + k0 + u) : 0.f;
             uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             *reinterpret_cast<uint4*>(sm + w_off + kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
         }
@@ -195,28 +242,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 #define TC_DBG(slot, val) do { if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 16 + (slot)] = (val); } while (0)
-    TC_DBG(0, 0x100u | tmem_base);
 #define TC_TRACE(role, idx) do { if (P.dbg && blockIdx.x == 0 && (tid & 31) == 0 && (idx) < 64) { unsigned t_; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_)); P.dbg[148 * 16 + (role) * 64 + (idx)] = t_; } } while (0)
+    TC_DBG(0, 0x100u | tmem_base);
     TC_TRACE(0, 0);
     const int ntiles = (N + TILE_M - 1) / TILE_M;
     const int acc_stride = P.tmem_cols >> 1;                // columns per accumulator stage
 
-    float st_s[MAXG / 2], st_ss[MAXG / 2];
-#pragma unroll
-    for (int g = 0; g < MAXG / 2; ++g) { st_s[g] = 0.f; st_ss[g] = 0.f; }
-
     if (warp >= NEPI / 32 && warp < MMA_WARP) {
         // =========================================================================== producers
-        // The A tile is stored MN-major (pixel-contiguous), exactly like the NCHW source: a thread moves 8
-        // consecutive pixels of one channel (two 16-byte global loads -> 8 bf16 -> one 16-byte shared store), a
-        // half-warp covers the 512 contiguous bytes a channel contributes to the tile.  Units (tile, K block) are
-        // streamed two deep: the loads of unit u+1 are issued before unit u is converted and stored.
-        // Shared layout of a stage (canonical UMMA MN-major, SWIZZLE_128B): 1024-byte atoms of 8 channels x 64
-        // pixels; atom(mblk, kblk) at mblk*8192 + kblk*1024; inside: channel (k&7)*128 B, 16-byte chunk j = (pixel%64)/8
-        // stored at chunk position j ^ (k&7).
+        // Shared layout of a ring slot (canonical UMMA MN-major, SWIZZLE_128B): 1024-byte atoms of 8 channels x 64
+        // pixels; atom(mblk, kblk) at mblk*8192 + kblk*1024; inside: channel (k&7)*128 B, 16-byte chunk
+        // j = (pixel%64)/8 stored at chunk position j ^ (k&7).  Units (tile, K block) are streamed two deep.
         const int pt = tid - NEPI;
         const Segs& S = P.seg;
-        struct Buf { float v[2][8]; float g[GATED ? 2 : 1][GATED ? 8 : 1]; int gch[2]; };
+        struct Buf { float v[2][8]; float g[GATED ? 2 : 1][8]; int gch[2]; };
         int trace_i = 0;
 
         auto issue = [&](int tile, int kb, Buf& b) {
@@ -231,29 +270,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 if (ch < kvalid && k < K && p < N) {
                     const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
                     const int cc = k - (sg == 0 ? 0 : S.cend[sg - 1]);
-                    const float* src = S.src[sg] + (long)cc * S.plane + p;
-                    const bool gated = GATED && sg == S.gate_seg;
-                    const float* gp = nullptr;
-                    if (gated) { b.gch[c] = S.gate_ch0 + cc; gp = S.gate_pre + (long)b.gch[c] * S.plane + p; }
-                    if (S.vec && p + 8 <= N) {
-                        const float4 lo = __ldg(reinterpret_cast<const float4*>(src));
-                        const float4 hi = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                        b.v[c][0] = lo.x; b.v[c][1] = lo.y; b.v[c][2] = lo.z; b.v[c][3] = lo.w;
-                        b.v[c][4] = hi.x; b.v[c][5] = hi.y; b.v[c][6] = hi.z; b.v[c][7] = hi.w;
-                        if constexpr (GATED) {
-                            if (gated) {
-                                const float4 glo = __ldg(reinterpret_cast<const float4*>(gp));
-                                const float4 ghi = __ldg(reinterpret_cast<const float4*>(gp) + 1);
-                                b.g[c][0] = glo.x; b.g[c][1] = glo.y; b.g[c][2] = glo.z; b.g[c][3] = glo.w;
-                                b.g[c][4] = ghi.x; b.g[c][5] = ghi.y; b.g[c][6] = ghi.z; b.g[c][7] = ghi.w;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const bool in = p + u < N;
-                            b.v[c][u] = in ? __ldg(src + u) : 0.f;
-                            if constexpr (GATED) { if (gated) b.g[c][u] = in ? __ldg(gp + u) : 0.f; }
+                    const int nvalid = (N - p >= 8) ? 8 : (int)(N - p);
+                    load8(S.src[sg], S.kind[sg], (long)cc * S.plane + p, nvalid, b.v[c]);
+                    if constexpr (GATED) {
+                        if (sg == S.gate_seg) {
+                            b.gch[c] = S.gate_ch0 + cc;
+                            load8(S.gate_pre, 1, (long)b.gch[c] * S.plane + p, nvalid, b.g[c]);
                         }
                     }
                 } else {
@@ -336,7 +358,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                     umma_commit(empty0 + 8 * stage);         // frees the ring slot when these MMAs retire
                 }
                 __syncwarp();
-                TC_DBG(5, (unsigned)(tile * 100 + kb + 1));
                 if (++stage == P.nstage) { stage = 0; phase ^= 1; }
             }
             if (lane == 0) umma_commit(tfull0 + 8 * as);     // accumulator complete -> epilogue
@@ -347,6 +368,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     } else {
         // =========================================================================== epilogue (warps 0-7)
         // warp w: TMEM lanes 32*(w&3).. (pixels), 32-column groups g = (w>>2), (w>>2)+2, ... (output channels)
+        float st_s[MAXG / 2], st_ss[MAXG / 2];
+#pragma unroll
+        for (int g = 0; g < MAXG / 2; ++g) { st_s[g] = 0.f; st_ss[g] = 0.f; }
         int as = 0; uint32_t aphase = 0;
         const int ng = NOUT >> 5;
         const int lq = warp & 3, ghalf = warp >> 2;
@@ -355,6 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             const long p = (long)tile * TILE_M + row;
             const bool valid = p < N;
             const float vmask = valid ? 1.f : 0.f;
+            const long pc = valid ? p : 0;
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             if (warp == 0) TC_TRACE(3, (tile - (int)blockIdx.x) / (int)gridDim.x);
@@ -366,12 +391,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                     float v[32];
                     tmem_ld32(t_addr + g * 32, v);
                     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                    float* o = P.out + (long)(g * 32) * P.out_plane + (valid ? p : 0);
+                    __nv_bfloat16* o = P.out + (long)(g * 32) * P.out_plane + pc;
                     const float* bs = sbias + g * 32;
+                    if (P.addend != nullptr) {
+                        const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(ad[(long)i * P.out_plane]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
                         const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
-                        if (valid) { o[0] = y0; o[P.out_plane] = y1; }
+                        if (valid) { o[0] = __float2bfloat16(y0); o[P.out_plane] = __float2bfloat16(y1); }
                         o += 2 * P.out_plane;
                         s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
                     }
@@ -396,7 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     tc_fence_before();
     if (tid == 0) TC_TRACE(5, 0);
     __syncthreads();
-    if (tid < (NOUT >> 5)) {
+    if (tid < P.nstat) {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) { a += red[0][w][tid]; b += red[1][w][tid]; }
