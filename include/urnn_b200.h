@@ -42,9 +42,9 @@ extern "C" {
 #define URNN_CELL_DECODER 1    /* hidden = cat(e,d) (2F ch)  : gates from cat(x,e,d)   */
 
 /* arithmetic of the gate contractions */
-#define URNN_MATH_FP32 0       /* fp32 FFMA, fp32 accumulate: the parity mode (atol 1e-5 vs reference)   */
-#define URNN_MATH_TF32 1       /* tcgen05 kind::tf32 on fp32 tiles, fp32 accumulate in TMEM              */
-#define URNN_MATH_BF16 2       /* tcgen05 kind::f16 on bf16-rounded tiles, fp32 accumulate in TMEM       */
+#define URNN_MATH_FP32 0       /* fp32 FFMA, fp32 accumulate: the parity mode (atol 1e-5 vs reference)                */
+#define URNN_MATH_BF16 2       /* tcgen05 kind::f16: GEMM operands rounded to bf16, fp32 accumulate in TMEM, fp32     */
+                               /* statistics / states; applies to the cell contractions and the stage stems (k=1)     */
 
 int         urnn_abi_version(void);
 const char* urnn_last_error(void);
@@ -103,7 +103,7 @@ int urnn_cgru_bwd(const urnn_cell_desc* d, const urnn_cell_params* p,
  * ------------------------------------------------------------------------------------------------ */
 /* y = [AvgPool2](LeakyReLU(conv1x1(x)+b, slope)).  pool = 1 (none) or 2 (AvgPool2d(2,2) AFTER the
  * activation, utils.py:92-94 layer order; needs H,W even).  x (Cin,H,W) -> y (Cout,H/pool,W/pool). */
-int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool, float slope,
+int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool, float slope, int32_t math,
                            const float* x, const float* w, const float* b, float* y, void* stream);
 /* dx overwritten (may be NULL); dw,db accumulated (may be NULL). */
 size_t urnn_conv1x1_lrelu_bwd_workspace_bytes(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool);
@@ -112,7 +112,7 @@ int urnn_conv1x1_lrelu_bwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int3
                            float* dx, float* dw, float* db, void* ws, size_t ws_bytes, void* stream);
 
 /* y = LeakyReLU(ConvTranspose2d(k=2,s=2,p=0)(x)+b): x (Cin,H,W), w (Cin,Cout,2,2) -> y (Cout,2H,2W). */
-int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope,
+int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope, int32_t math,
                              const float* x, const float* w, const float* b, float* y, void* stream);
 size_t urnn_deconv2x2_lrelu_bwd_workspace_bytes(int32_t Cin, int32_t Cout, int32_t H, int32_t W);
 int urnn_deconv2x2_lrelu_bwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope,

@@ -103,12 +103,14 @@ def avg_pool2(x):
     return v.mean(axis=(2, 4)).astype(x.dtype)
 
 
-def conv_transpose2x2(x, w, b):
+def conv_transpose2x2(x, w, b, quant=None):
     """nn.ConvTranspose2d(k=2, s=2, p=0): non-overlapping 2x upsample.  utils.py:95-100.
     x (Cin,H,W), w (Cin,Cout,2,2) -> (Cout,2H,2W)."""
     cin, cout, kh, kw = w.shape
     c, h, wd = x.shape
     assert c == cin and kh == 2 and kw == 2
+    if quant == "bf16":
+        x, w = round_bf16(x), round_bf16(w)
     y = np.zeros((cout, 2 * h, 2 * wd), dtype=x.dtype)
     xf = x.reshape(cin, h * wd)
     for dy in range(2):
@@ -197,7 +199,7 @@ def encoder_step(p, x, enc_states, down_factors=(1, 2, 2), quant=None):
     cur = x
     for k in range(3):
         key = ENC_STEM_KEYS[k]
-        cur = leaky_relu(conv2d_same(cur, p[key + ".weight"], p[key + ".bias"]))
+        cur = leaky_relu(conv2d_same(cur, p[key + ".weight"], p[key + ".bias"], quant))
         if down_factors[k] > 1:
             cur = avg_pool2(cur)
         F = enc_states[k].shape[0]
@@ -222,9 +224,9 @@ def decoder_step(p, enc_states, dec_states, quant=None):
         key = DEC_STEM_KEYS[stage]
         w, b = p[key + ".weight"], p[key + ".bias"]
         if "deconv" in key:
-            cur = leaky_relu(conv_transpose2x2(h, w, b))             # utils.py:95-107
+            cur = leaky_relu(conv_transpose2x2(h, w, b, quant))      # utils.py:95-107
         else:
-            cur = leaky_relu(conv2d_same(h, w, b))
+            cur = leaky_relu(conv2d_same(h, w, b, quant))
     return cur, new_states
 
 

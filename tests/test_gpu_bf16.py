@@ -72,3 +72,53 @@ def test_bf16_ed_sequence_tracks_fp32(golden_dir):
     rms = np.sqrt(np.mean((d32 - d16)[both] ** 2))
     assert rms <= 2e-2 * np.sqrt(np.mean(d32[both] ** 2)) + 1e-3
     assert np.mean((d32 != 0) != (d16 != 0)) <= 1e-2
+
+
+def test_bf16_stems_vs_quantised_oracle():
+    """tcgen05 stems: operands rounded to bf16, fp32 accumulate, LeakyReLU / AvgPool2 / 2x2 scatter in fp32."""
+    from urnn_b200 import ops
+    rng = np.random.RandomState(0)
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    for cin, cout, H, W, pool in [(63, 16, 20, 24, 1), (9, 16, 8, 132, 1), (64, 64, 12, 20, 2), (96, 96, 10, 8, 2),
+                                  (64, 16, 4, 4, 1), (7, 40, 6, 8, 2), (96, 96, 250, 250, 2), (5, 16, 7, 9, 1)]:
+        x = rng.randn(cin, H, W).astype(np.float32)
+        w = (rng.randn(cout, cin, 1, 1) / np.sqrt(cin)).astype(np.float32)
+        b = rng.randn(cout).astype(np.float32)
+        y = ops.conv1x1_lrelu_fwd(t(x), t(w), t(b), pool, math="bf16").cpu().numpy()
+        ref = O.leaky_relu(O.conv2d_same(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), "bf16"))
+        if pool == 2:
+            ref = O.avg_pool2(ref)
+        np.testing.assert_allclose(y, ref, atol=2e-5, rtol=1e-4)
+    for cin, cout, H, W in [(96, 96, 8, 8), (96, 96, 5, 12), (32, 8, 3, 4), (96, 96, 125, 125), (8, 8, 3, 5), (16, 100, 6, 6)]:
+        x = rng.randn(cin, H, W).astype(np.float32)
+        w = (rng.randn(cin, cout, 2, 2) / np.sqrt(cin)).astype(np.float32)
+        b = rng.randn(cout).astype(np.float32)
+        y = ops.deconv2x2_lrelu_fwd(t(x), t(w), t(b), math="bf16").cpu().numpy()
+        ref = O.leaky_relu(O.conv_transpose2x2(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64), "bf16"))
+        np.testing.assert_allclose(y, ref, atol=2e-5, rtol=1e-4)
+
+
+def test_bf16_ed_fused_equals_module_route_and_tracks_model():
+    """bf16 mode: the single-call route (bf16 stem maps) and the per-module route (fp32 stem maps, rounded by the
+    consumer) are numerically the same computation; both follow the oracle's model of the mode."""
+    from src.lib.model.networks.model import ED
+    from src.lib.model.networks.net_params import get_network_params
+    H, W = 32, 48
+    torch.manual_seed(0)
+    enc, dec = get_network_params(False, H, W, input_channels=9, math="bf16")
+    net = ED(False, enc, dec, 0.5, False, input_height=H, input_width=W).to(DEV).eval()
+    xs = torch.from_numpy(O.synthetic_event_inputs(H, W, 2, 3)).to(DEV)
+    torch.manual_seed(5)
+    st = [torch.rand(1, *s.shape, device=DEV) for s in O.zero_states(H, W)]
+    with torch.no_grad():
+        a = net(xs[1][None, None], *st)
+        enc_s = net.encoder(xs[1][None, None].permute(1, 0, 2, 3, 4), st[:3])
+        feat, dec_s = net.decoder(enc_s, st[3:])
+        out = net.head(feat)[:, :, 0]
+    for u, v in zip(a, (out, *enc_s, *dec_s)):
+        assert torch.equal(u, v)
+    w = {k: v.detach().cpu().numpy().astype(np.float64) for k, v in net.state_dict().items()}
+    res = O.ed_step(w, xs[1].cpu().numpy().astype(np.float64), [s.cpu().numpy()[0].astype(np.float64) for s in st], quant="bf16")
+    for i in range(6):
+        d = np.abs(a[1 + i].cpu().numpy()[0] - res["states"][i])
+        assert d.max() <= 2e-2 and d.mean() <= 1e-4, (i, d.max(), d.mean())

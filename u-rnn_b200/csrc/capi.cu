@@ -56,7 +56,7 @@ int urnn_cgru_fwd(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     switch (d->math) {
         case URNN_MATH_FP32: return cgru_fwd_fp32(d, p, x, e, h, h_out, ws, ws_bytes, st);
 #ifndef URNN_NO_TC
-        case URNN_MATH_BF16: return cgru_fwd_bf16(d, p, x, e, h, h_out, ws, ws_bytes, st);
+        case URNN_MATH_BF16: return cgru_fwd_bf16(d, p, x, 0, e, h, h_out, ws, ws_bytes, st);
 #endif
         default: set_error("cgru_fwd: math mode %d not built", d->math); return URNN_E_UNSUPPORTED;
     }
@@ -68,13 +68,17 @@ int urnn_cgru_bwd(const urnn_cell_desc*, const urnn_cell_params*, const float*, 
     set_error("cgru_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
 }
 
-int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool, float slope,
+int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool, float slope, int32_t math,
                            const float* x, const float* w, const float* b, float* y, void* stream) {
     URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0, "conv1x1: bad shape");
     URNN_CHECK_ARG(pool == 1 || pool == 2, "conv1x1: pool must be 1 or 2");
     URNN_CHECK_ARG(pool == 1 || (W % 2 == 0 && H % 2 == 0), "conv1x1: AvgPool2 needs even H=%d, W=%d", H, W);
     URNN_CHECK_ARG(pool == 1 || (reinterpret_cast<uintptr_t>(x) & 7) == 0, "conv1x1: pooled input must be 8-byte aligned");
     URNN_CHECK_ARG(x && w && b && y, "conv1x1: null pointer");
+#ifndef URNN_NO_TC
+    if (math == URNN_MATH_BF16 && Cout <= 256)
+        return conv1x1_lrelu_fwd_tc(Cin, Cout, H, W, pool, slope, x, 0, w, b, nullptr, y, (cudaStream_t)stream);
+#endif
     return conv1x1_lrelu_fwd_fp32(Cin, Cout, H, W, pool, slope, x, w, b, y, (cudaStream_t)stream);
 }
 size_t urnn_conv1x1_lrelu_bwd_workspace_bytes(int32_t, int32_t, int32_t, int32_t, int32_t) { return 0; }
@@ -83,11 +87,15 @@ int urnn_conv1x1_lrelu_bwd(int32_t, int32_t, int32_t, int32_t, int32_t, float, c
     set_error("conv1x1_lrelu_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
 }
 
-int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope, const float* x,
+int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope, int32_t math, const float* x,
                              const float* w, const float* b, float* y, void* stream) {
     URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0, "deconv2x2: bad shape");
     URNN_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 7) == 0, "deconv2x2: output must be 8-byte aligned");
     URNN_CHECK_ARG(x && w && b && y, "deconv2x2: null pointer");
+#ifndef URNN_NO_TC
+    if (math == URNN_MATH_BF16)
+        return deconv2x2_lrelu_fwd_tc(Cin, Cout, H, W, slope, x, 0, w, b, nullptr, y, (cudaStream_t)stream);
+#endif
     return deconv2x2_lrelu_fwd_fp32(Cin, Cout, H, W, slope, x, w, b, y, (cudaStream_t)stream);
 }
 size_t urnn_deconv2x2_lrelu_bwd_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
@@ -168,27 +176,34 @@ int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float
     if (pl.total > ws_bytes) { set_error("ed_step: workspace %zu < %zu bytes", ws_bytes, pl.total); return URNN_E_WORKSPACE; }
     for (int i = 0; i < 6; ++i) URNN_CHECK_ARG(sin[i] && sout[i] && sin[i] != sout[i], "ed_step: state %d null or aliased", i);
     const float sl = d->lrelu_slope;
-    // ---- encoder (encoder.py:187-215): stem conv (+pool) then ConvGRU, stage k feeds stage k+1
-    const float* cur = input; int cin = d->Cin;
-    for (int k = 0; k < 3; ++k) {
-        int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
-        URNN_TRY(urnn_conv1x1_lrelu_fwd(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, p->enc_stem_w[k],
-                                        p->enc_stem_b[k], pl.s[k], stream));
-        URNN_TRY(urnn_cgru_fwd(&pl.enc[k], &p->enc_cell[k], pl.s[k], nullptr, sin[k], sout[k], pl.cell_ws,
-                               pl.cell_ws_bytes, stream));
-        cur = sout[k]; cin = d->enc_gru[k];
+    cudaStream_t st = (cudaStream_t)stream;
+#ifndef URNN_NO_TC
+    if (d->math == URNN_MATH_BF16) {
+        // tcgen05 route: stem outputs that only feed GEMMs are kept as bf16 maps (the consumer would round them anyway)
+        __nv_bfloat16* sb[3] = {(__nv_bfloat16*)pl.s[0], (__nv_bfloat16*)pl.s[1], (__nv_bfloat16*)pl.s[2]};
+        __nv_bfloat16 *up3 = (__nv_bfloat16*)pl.up3, *up2 = (__nv_bfloat16*)pl.up2;
+        const float* cur = input; int cin = d->Cin;
+        for (int k = 0; k < 3; ++k) {
+            int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
+            URNN_TRY(conv1x1_lrelu_fwd_tc(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, 0, p->enc_stem_w[k],
+                                          p->enc_stem_b[k], sb[k], nullptr, st));
+            URNN_TRY(check_cell(&pl.enc[k], &p->enc_cell[k], nullptr, sin[k], sout[k]));
+            URNN_TRY(cgru_fwd_bf16(&pl.enc[k], &p->enc_cell[k], sb[k], 1, nullptr, sin[k], sout[k], pl.cell_ws, pl.cell_ws_bytes, st));
+            cur = sout[k]; cin = d->enc_gru[k];
+        }
+        URNN_TRY(cgru_fwd_bf16(&pl.dec[0], &p->dec_cell[0], nullptr, 0, sout[2], sin[3], sout[3], pl.cell_ws, pl.cell_ws_bytes, st));
+        URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[0], d->dec_conv[0], pl.h[2], pl.w[2], sl, sout[3], 0, p->dec_stem_w[0],
+                                        p->dec_stem_b[0], up3, nullptr, st));
+        URNN_TRY(cgru_fwd_bf16(&pl.dec[1], &p->dec_cell[1], up3, 1, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, st));
+        URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, sout[4], 0, p->dec_stem_w[1],
+                                        p->dec_stem_b[1], up2, nullptr, st));
+        URNN_TRY(cgru_fwd_bf16(&pl.dec[2], &p->dec_cell[2], up2, 1, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, st));
+        URNN_TRY(conv1x1_lrelu_fwd_tc(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], 0, p->dec_stem_w[2], p->dec_stem_b[2],
+                                      nullptr, pl.feat, st));
+        return urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream);
     }
-    // ---- decoder (decoder.py:173-217): deepest first; x of the deepest stage is None -> zeros
-    URNN_TRY(urnn_cgru_fwd(&pl.dec[0], &p->dec_cell[0], nullptr, sout[2], sin[3], sout[3], pl.cell_ws, pl.cell_ws_bytes, stream));
-    URNN_TRY(urnn_deconv2x2_lrelu_fwd(d->dec_gru[0], d->dec_conv[0], pl.h[2], pl.w[2], sl, sout[3], p->dec_stem_w[0],
-                                      p->dec_stem_b[0], pl.up3, stream));
-    URNN_TRY(urnn_cgru_fwd(&pl.dec[1], &p->dec_cell[1], pl.up3, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, stream));
-    URNN_TRY(urnn_deconv2x2_lrelu_fwd(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, sout[4], p->dec_stem_w[1],
-                                      p->dec_stem_b[1], pl.up2, stream));
-    URNN_TRY(urnn_cgru_fwd(&pl.dec[2], &p->dec_cell[2], pl.up2, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, stream));
-    URNN_TRY(urnn_conv1x1_lrelu_fwd(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], p->dec_stem_w[2], p->dec_stem_b[2],
-                                    pl.feat, stream));
-    // ---- head (flood_head.py:131-177)
+#endif
+    // ---- encoder    // ---- head (flood_head.py:131-177)
     URNN_TRY(urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream));
     return URNN_OK;
 }

@@ -15,20 +15,26 @@
 namespace urnn {
 
 static int g_num_sms = 0;
-static bool g_attr_set[2] = {false, false};
 
-static int tc_launch(tc::GemmParams& P, cudaStream_t st) {
+template <bool GATED, int EPI>
+static int tc_launch_t(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<GATED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+        attr_set = true;
+    }
+    tc::gemm_gn_kernel<GATED, EPI><<<grid, tc::NTHREADS, smem, st>>>(P);
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
+
+int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
     if (g_num_sms == 0) {
         int dev = 0;
         URNN_CUDA(cudaGetDevice(&dev));
         URNN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const bool gated = P.seg.gate_seg >= 0;
-    if (!g_attr_set[gated]) {
-        if (gated) URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
-        else       URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
-        g_attr_set[gated] = true;
-    }
     int nstage = 0;
     size_t smem = tc::gemm_smem_bytes(P.NOUT, P.K, &nstage);
     if (smem == 0) { set_error("tc gemm: weights %dx%d do not fit in shared memory", P.NOUT, P.K); return URNN_E_UNSUPPORTED; }
@@ -39,9 +45,58 @@ static int tc_launch(tc::GemmParams& P, cudaStream_t st) {
     P.dbg = nullptr;
     int ntiles = (P.N + tc::TILE_M - 1) / tc::TILE_M;
     int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
-    if (gated) tc::gemm_gn_kernel<true><<<grid, tc::NTHREADS, smem, st>>>(P);
-    else       tc::gemm_gn_kernel<false><<<grid, tc::NTHREADS, smem, st>>>(P);
-    URNN_LAUNCH_CHECK();
+    switch (epi) {
+        case tc::EPI_GN:     return gated ? tc_launch_t<true, tc::EPI_GN>(P, grid, smem, st) : tc_launch_t<false, tc::EPI_GN>(P, grid, smem, st);
+        case tc::EPI_LRELU:  return tc_launch_t<false, tc::EPI_LRELU>(P, grid, smem, st);
+        case tc::EPI_POOL:   return tc_launch_t<false, tc::EPI_POOL>(P, grid, smem, st);
+        case tc::EPI_DECONV: return tc_launch_t<false, tc::EPI_DECONV>(P, grid, smem, st);
+    }
+    set_error("tc gemm: bad epilogue %d", epi);
+    return URNN_E_INVALID;
+}
+
+void tc_params_defaults(tc::GemmParams& P) {
+    P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
+    for (int i = 0; i < 3; ++i) { P.seg.src[i] = nullptr; P.seg.cend[i] = 0; P.seg.kind[i] = 0; }
+    P.w_ks = 1; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0; P.bias = nullptr; P.nbias = 0;
+    P.out = nullptr; P.out_f32 = nullptr; P.addend = nullptr; P.nstat = 0; P.slope = 0.f; P.img_w = 0; P.n_base = 0;
+    P.sink = StatSink{nullptr, nullptr, nullptr, 0, 0};
+    P.aff = AffineOut{nullptr, nullptr, nullptr, nullptr, 0, 32, 1.0, 0.f};
+    P.dbg = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------ stems on tcgen05
+// y = [AvgPool2](LeakyReLU(conv1x1(x) + b)); x fp32 (kind 0) or bf16 (kind 1); exactly one of y_bf16 / y_f32 is set
+int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope, const void* x, int xkind,
+                         const float* w, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st) {
+    if (Cout > 256) { set_error("conv1x1(bf16): Cout=%d > 256", Cout); return URNN_E_UNSUPPORTED; }
+    if (pool == 2 && xkind != 0) { set_error("conv1x1(bf16): pooled stem needs an fp32 source"); return URNN_E_UNSUPPORTED; }
+    tc::GemmParams P; tc_params_defaults(P);
+    P.seg.src[0] = P.seg.src[1] = P.seg.src[2] = x; P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = xkind;
+    P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = Cin; P.seg.plane = (long)H * W;
+    P.W = w; P.w_ld = Cin; P.w_ks = 1; P.nrow1 = 1 << 30;
+    P.bias = b; P.nbias = Cout; P.NOUT = (Cout + 31) & ~31; P.nout_store = Cout; P.K = Cin;
+    P.out = y_bf16; P.out_f32 = y_f32; P.slope = slope;
+    if (pool == 1) { P.N = H * W; P.out_plane = (long)H * W; return tc_launch(P, tc::EPI_LRELU, st); }
+    P.N = 4 * (H / 2) * (W / 2); P.out_plane = (long)(H / 2) * (W / 2); P.img_w = W;
+    return tc_launch(P, tc::EPI_POOL, st);
+}
+
+// y = LeakyReLU(ConvTranspose2d(k2,s2)(x) + b): GEMM rows n = co*4 + dy*2 + dx, split into launches of <= 256 rows
+int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const void* x, int xkind, const float* w,
+                           const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st) {
+    const int M = 4 * Cout;
+    int per = 256;
+    if (M <= 256) per = (M + 31) & ~31; else if (M % 192 == 0) per = 192; else if (M % 128 == 0) per = 128;
+    for (int n0 = 0; n0 < M; n0 += per) {
+        tc::GemmParams P; tc_params_defaults(P);
+        P.seg.src[0] = P.seg.src[1] = P.seg.src[2] = x; P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = xkind;
+        P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = Cin; P.seg.plane = (long)H * W;
+        P.W = w + n0; P.w_ld = 1; P.w_ks = M; P.nrow1 = 1 << 30;
+        P.bias = b; P.NOUT = per; P.nout_store = (M - n0 < per) ? (M - n0) : per; P.K = Cin; P.N = H * W;
+        P.out = y_bf16; P.out_f32 = y_f32; P.out_plane = (long)4 * H * W; P.slope = slope; P.img_w = W; P.n_base = n0;
+        URNN_TRY(tc_launch(P, tc::EPI_DECONV, st));
+    }
     return URNN_OK;
 }
 
@@ -95,9 +150,12 @@ static size_t cell_ws_bf16(const urnn_cell_desc* d, void* ws, size_t ws_bytes, C
     return align_up(a.off, 256);
 }
 
-int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    if (d->ksize != 1) return cgru_fwd_fp32(d, p, x, e, h, h_out, ws, ws_bytes, st);   // k>1: fp32 taps path
+    if (d->ksize != 1) {                                                                 // k>1: fp32 taps path
+        if (xkind != 0) { set_error("cgru_fwd: bf16 x needs k=1"); return URNN_E_UNSUPPORTED; }
+        return cgru_fwd_fp32(d, p, (const float*)x, e, h, h_out, ws, ws_bytes, st);
+    }
     const int F = d->F;
     const long N = (long)d->H * d->W;
     const int Ch = (d->variant == URNN_CELL_DECODER) ? 2 * F : F;
@@ -113,14 +171,14 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     if (need > ws_bytes) { set_error("cgru_fwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
     URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
 
-    tc::GemmParams P;
+    tc::GemmParams P; tc_params_defaults(P);
     // segments [x | e | h]; missing ones get zero width
-    int n = 0; const float* srcs[3] = {h, h, h}; int cnt[3] = {0, 0, 0};
-    if (x) { srcs[n] = x; cnt[n] = d->Cx; ++n; }
+    int n = 0; const void* srcs[3] = {h, h, h}; int cnt[3] = {0, 0, 0}; int kinds[3] = {0, 0, 0};
+    if (x) { srcs[n] = x; cnt[n] = d->Cx; kinds[n] = xkind; ++n; }
     if (d->variant == URNN_CELL_DECODER) { srcs[n] = e; cnt[n] = F; ++n; }
     srcs[n] = h; cnt[n] = F; const int hseg = n; ++n;
     int acc = 0;
-    for (int i = 0; i < 3; ++i) { P.seg.src[i] = srcs[i]; P.seg.kind[i] = 0; acc += cnt[i]; P.seg.cend[i] = acc; }
+    for (int i = 0; i < 3; ++i) { P.seg.src[i] = srcs[i]; P.seg.kind[i] = kinds[i]; acc += cnt[i]; P.seg.cend[i] = acc; }
     P.seg.plane = N;
     P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
     P.N = (int)N; P.K = Keff; P.out_plane = N; P.addend = nullptr;
@@ -129,16 +187,17 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     P.W = p->w1 + aoff; P.w_ld = Ktot; P.nrow1 = 2 * F;
     P.W2 = p->w2 + aoff; P.w2_ld = Ktot; P.k2 = Kxe;
     P.bias = p->b1; P.nbias = 2 * F;
-    P.NOUT = split ? 3 * F : 2 * F;
+    P.NOUT = split ? 3 * F : 2 * F; P.nout_store = P.NOUT;
     P.out = w.GP; P.nstat = 2 * F / 32;
     P.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx};
     P.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, 32.0 * (double)N, d->eps};
-    URNN_TRY(tc_launch(P, st));
+    URNN_TRY(tc_launch(P, tc::EPI_GN, st));
 
     // ---- sweep B
     P.seg.gate_ch0 = F; P.seg.gate_pre = w.GP; P.seg.gate_scale = w.scale1; P.seg.gate_shift = w.shift1;
     if (split) {
-        P.seg.src[0] = h; P.seg.kind[0] = 0; P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = F;
+        P.seg.src[0] = P.seg.src[1] = P.seg.src[2] = h; P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = 0;
+        P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = F;
         P.seg.gate_seg = 0;
         P.K = F; P.W = p->w2 + aoff + Kxe;
         P.addend = w.GP + (size_t)2 * F * N;
@@ -147,10 +206,10 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
         P.W = p->w2 + aoff;
     }
     P.w_ld = Ktot; P.nrow1 = F; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0;
-    P.bias = p->b2; P.nbias = F; P.NOUT = F; P.out = w.C; P.nstat = F / 32;
+    P.bias = p->b2; P.nbias = F; P.NOUT = F; P.nout_store = F; P.out = w.C; P.nstat = F / 32;
     P.sink = StatSink{w.partial2, w.total2, w.counter + 1, F / 32, w.gx};
     P.aff = AffineOut{w.scale2, w.shift2, p->gn2_w, p->gn2_b, F, 32, 32.0 * (double)N, d->eps};
-    URNN_TRY(tc_launch(P, st));
+    URNN_TRY(tc_launch(P, tc::EPI_GN, st));
 
     // ---- sweep C
     const long nquad = (long)F * N / 4;

@@ -38,7 +38,7 @@ __device__ __forceinline__ void ln_silu16(float (&v)[16], float mean, float rstd
     for (int c = 0; c < 16; ++c) {
         float g = __ldg(lw + c * plane + pix), b = __ldg(lb + c * plane + pix);
         float y = fmaf((v[c] - mean) * rstd, g, b);
-        v[c] = silu_acc(y);
+        v[c] = silu_fast(y);
     }
 }
 
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) head_kernel(HeadDev hd, const float* __re
                     float pc = __ldg(hd.p.cls_pred_b), pr = __ldg(hd.p.reg_pred_b);
 #pragma unroll
                     for (int c = 0; c < 16; ++c) { pc = fmaf(pw[0][c], vc[c], pc); pr = fmaf(pw[1][c], vr[c], pr); }
-                    float prob = sigmoid_acc(pc);
+                    float prob = sigmoid_fast(pc);
                     float depth = lrelu(pr, hd.slope);
                     out[pix] = (prob >= hd.cls_thred) ? depth : depth * 0.0f;   // depth * mask, flood_head.py:201-202
                     out[plane + pix] = prob;

@@ -175,21 +175,46 @@ struct Segs {
 struct GemmParams {
     Segs seg;
     // weights: row n < nrow1 is W[n*w_ld + k]; row n >= nrow1 is W2[(n-nrow1)*w2_ld + k] for k < k2 and 0 beyond
-    const float* W; long w_ld; int nrow1;
+    const float* W; long w_ld; long w_ks; int nrow1;   // element (n,k) = W[n*w_ld + k*w_ks]
     const float* W2; long w2_ld; int k2;
     const float* bias; int nbias;            // bias[n] for n < nbias, zero beyond
     int NOUT, K, N;                          // output channels (multiple of 32, <= 256), reduction size, pixels
     __nv_bfloat16* out; long out_plane;      // bf16 NCHW destination of (acc + bias [+ addend])
     const __nv_bfloat16* addend;             // optional bf16 map [NOUT][plane] added before store / statistics
     int nstat;                               // leading 32-channel groups whose (sum, sumsq) go to `sink`
+    // stem epilogues (EPI_LRELU / EPI_POOL / EPI_DECONV)
+    int nout_store;                          // columns actually stored (<= NOUT; NOUT is padded to 32)
+    float* out_f32;                          // fp32 destination instead of `out` when non-null (EPI_LRELU)
+    float slope;                             // LeakyReLU slope
+    int img_w;                               // EPI_POOL: input width (producer gathers 2x2 quads); EPI_DECONV: input width
+    int n_base;                              // EPI_DECONV: global column offset of this launch (n = co*4 + dy*2 + dx)
     StatSink sink; AffineOut aff;
     int nstage;                              // K-block ring depth
     int tmem_cols;                           // power of two >= 2 * NOUT
     volatile unsigned* dbg;                  // optional host-mapped progress / trace words (bring-up only)
 };
 
+enum { EPI_GN = 0, EPI_LRELU = 1, EPI_POOL = 2, EPI_DECONV = 3 };
+
+// 8 tile slots = 2 pooling quads (slot = 4*quad + 2*dy + dx) gathered from an fp32 map of width img_w
+__device__ __forceinline__ void load8_quads(const float* plane_base, long q0, long nquads, int w2, int img_w, float (&v)[8]) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const long Q = q0 + t;
+        if (Q < nquads) {
+            const long qy = Q / w2, qx = Q % w2;
+            const float* b = plane_base + (2 * qy) * (long)img_w + 2 * qx;
+            const float2 top = __ldg(reinterpret_cast<const float2*>(b));
+            const float2 bot = __ldg(reinterpret_cast<const float2*>(b + img_w));
+            v[4 * t + 0] = top.x; v[4 * t + 1] = top.y; v[4 * t + 2] = bot.x; v[4 * t + 3] = bot.y;
+        } else {
+            v[4 * t + 0] = v[4 * t + 1] = v[4 * t + 2] = v[4 * t + 3] = 0.f;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
-template <bool GATED>
+template <bool GATED, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -220,7 +245,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
-    for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = (i < P.nbias) ? __ldg(P.bias + i) : 0.f;
+    if constexpr (EPI == EPI_DECONV) {
+        for (int i = tid; i < (NOUT >> 2); i += NTHREADS) sbias[i] = (4 * i < P.nout_store) ? __ldg(P.bias + ((P.n_base >> 2) + i)) : 0.f;
+    } else {
+        for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = (i < P.nbias) ? __ldg(P.bias + i) : 0.f;
+    }
     {
         const int chunks_per_row = nkb * 8;                 // 16-byte chunks (8 bf16) per weight row
         for (int idx = tid; idx < NOUT * chunks_per_row; idx += NTHREADS) {
@@ -231,7 +260,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             const int klim = second ? (P.k2 < K ? P.k2 : K) : K;
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim) ? __ldg(wrow + k0 + u) : 0.f;
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim && n < P.nout_store) ? __ldg(wrow + (long)(k0 + u) * (second ? 1 : P.w_ks)) : 0.f;
             uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             *reinterpret_cast<uint4*>(sm + w_off + kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
         }
@@ -271,7 +300,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                     const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
                     const int cc = k - (sg == 0 ? 0 : S.cend[sg - 1]);
                     const int nvalid = (N - p >= 8) ? 8 : (int)(N - p);
-                    load8(S.src[sg], S.kind[sg], (long)cc * S.plane + p, nvalid, b.v[c]);
+                    if constexpr (EPI == EPI_POOL) {
+                        load8_quads(reinterpret_cast<const float*>(S.src[sg]) + (long)cc * S.plane, p >> 2, (long)N >> 2,
+                                    P.img_w >> 1, P.img_w, b.v[c]);
+                    } else {
+                        load8(S.src[sg], S.kind[sg], (long)cc * S.plane + p, nvalid, b.v[c]);
+                    }
                     if constexpr (GATED) {
                         if (sg == S.gate_seg) {
                             b.gch[c] = S.gate_ch0 + cc;
@@ -390,22 +424,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 if (g < ng) {
                     float v[32];
                     tmem_ld32(t_addr + g * 32, v);
-                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                    __nv_bfloat16* o = P.out + (long)(g * 32) * P.out_plane + pc;
-                    const float* bs = sbias + g * 32;
-                    if (P.addend != nullptr) {
-                        const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
+                    if constexpr (EPI == EPI_GN) {
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        __nv_bfloat16* o = P.out + (long)(g * 32) * P.out_plane + pc;
+                        const float* bs = sbias + g * 32;
+                        if (P.addend != nullptr) {
+                            const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(ad[(long)i * P.out_plane]);
-                    }
+                            for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(ad[(long)i * P.out_plane]);
+                        }
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
-                        if (valid) { o[0] = __float2bfloat16(y0); o[P.out_plane] = __float2bfloat16(y1); }
-                        o += 2 * P.out_plane;
-                        s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+                        for (int i = 0; i < 32; i += 2) {
+                            const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
+                            if (valid) { o[0] = __float2bfloat16(y0); o[P.out_plane] = __float2bfloat16(y1); }
+                            o += 2 * P.out_plane;
+                            s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+                        }
+                        st_s[gi] += (s0 + s1) * vmask; st_ss[gi] += (q0 + q1) * vmask;
+                    } else if constexpr (EPI == EPI_LRELU) {
+                        // y = LeakyReLU(acc + bias) -> NCHW (bf16 or fp32)
+                        const float* bs = sbias + g * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int n = g * 32 + i;
+                            const float y = lrelu(v[i] + bs[i], P.slope);
+                            if (valid && n < P.nout_store) {
+                                if (P.out_f32) P.out_f32[(long)n * P.out_plane + p] = y;
+                                else P.out[(long)n * P.out_plane + p] = __float2bfloat16(y);
+                            }
+                        }
+                    } else if constexpr (EPI == EPI_POOL) {
+                        // tile slot = 4*quad + sub-pixel: AvgPool2 = mean over 4 consecutive lanes, after the activation
+                        const float* bs = sbias + g * 32;
+                        const long Q = p >> 2;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float y = lrelu(v[i] + bs[i], P.slope);
+                            y += __shfl_xor_sync(0xffffffffu, y, 1);
+                            y += __shfl_xor_sync(0xffffffffu, y, 2);
+                            const int n = g * 32 + i;
+                            if (valid && (lane & 3) == 0 && n < P.nout_store) {
+                                if (P.out_f32) P.out_f32[(long)n * P.out_plane + Q] = 0.25f * y;
+                                else P.out[(long)n * P.out_plane + Q] = __float2bfloat16(0.25f * y);
+                            }
+                        }
+                    } else {
+                        // ConvTranspose2d(k2,s2): column n = co*4 + dy*2 + dx of pixel (y,x) -> out[co][2y+dy][2x+dx]
+                        const long py = pc / P.img_w, px = pc % P.img_w;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const int n = P.n_base + g * 32 + i;            // dx = 0 (i even), partner i+1 has dx = 1
+                            const int co = n >> 2, dy = (n >> 1) & 1;
+                            const float b = sbias[(g * 32 + i) >> 2];
+                            const float y0 = lrelu(v[i] + b, P.slope), y1 = lrelu(v[i + 1] + b, P.slope);
+                            if (valid && g * 32 + i < P.nout_store) {
+                                const long off = (long)co * P.out_plane + (2 * py + dy) * (2L * P.img_w) + 2 * px;
+                                if (P.out_f32) *reinterpret_cast<float2*>(P.out_f32 + off) = make_float2(y0, y1);
+                                else *reinterpret_cast<uint32_t*>(P.out + off) = pack_bf16(y0, y1);
+                            }
+                        }
                     }
-                    st_s[gi] += (s0 + s1) * vmask; st_ss[gi] += (q0 + q1) * vmask;
                 }
             }
             tc_fence_before();
@@ -426,14 +504,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     tc_fence_before();
     if (tid == 0) TC_TRACE(5, 0);
     __syncthreads();
-    if (tid < P.nstat) {
+    if (EPI == EPI_GN && tid < P.nstat) {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) { a += red[0][w][tid]; b += red[1][w][tid]; }
         P.sink.partial[(size_t)tid * P.sink.stride + blockIdx.x] = make_float2(a, b);
     }
     if (warp == MMA_WARP) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
-    stats_finalize_last_cta(P.sink, gridDim.x, gridDim.x, &P.aff);
+    if constexpr (EPI == EPI_GN) stats_finalize_last_cta(P.sink, gridDim.x, gridDim.x, &P.aff);
 }
 
 // dynamic shared memory needed for a given problem; 0 if it cannot fit

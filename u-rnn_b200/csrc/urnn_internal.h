@@ -1,6 +1,7 @@
 // urnn_internal.h -- internal (C++) interfaces between the translation units of liburnn_b200.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include "../../include/urnn_b200.h"
 
 namespace urnn {
@@ -16,9 +17,14 @@ struct CellWsView {
 size_t cell_ws_view(const urnn_cell_desc* d, void* ws, size_t ws_bytes, CellWsView* out);
 int cgru_blend_launch(const CellWsView& w, const float* h, float* h_out, int F, long N, cudaStream_t st);
 
-// tcgen05 bf16 path (cgru_tc.cu)
-int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+// tcgen05 bf16 path (cgru_tc.cu).  x / stem inputs may be fp32 (kind 0) or bf16 (kind 1) maps; stem outputs go
+// to exactly one of y_bf16 / y_f32.
+int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope, const void* x, int xkind,
+                         const float* w, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
+int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const void* x, int xkind, const float* w,
+                           const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
 
 // fp32 FFMA path (urnn_fp32.cu)
 size_t cgru_fwd_fp32_workspace(const urnn_cell_desc* d);

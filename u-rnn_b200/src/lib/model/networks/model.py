@@ -26,6 +26,9 @@ class ED(nn.Module):
         self.head = YOLOXHead(cls_thred, use_checkpoint=use_checkpoint,
                               input_height=input_height, input_width=input_width)
         self._plan = None
+        for stems, cells in zip(self._stems(), self._cells()):      # stems follow the arithmetic mode of the cells
+            for stem, cell in zip(stems, cells):
+                stem.math = cell.math
 
     # ---- fused whole-step route --------------------------------------------------------------
     def _cells(self):

@@ -33,6 +33,7 @@ class StageStem(nn.Sequential):
         super().__init__(layers)
         self.kind = kind      # "conv" | "deconv"
         self.pool = pool      # 1 | 2 (AvgPool2d(2,2) after the activation)
+        self.math = None      # "fp32" | "bf16" | None (library default); ED copies it from its cells
 
     def _conv(self):
         for m in self.children():
@@ -46,9 +47,9 @@ class StageStem(nn.Sequential):
         outs = []
         for b in range(x.size(0)):
             if self.kind == "deconv":
-                outs.append(ops.deconv2x2_lrelu(x[b], conv.weight, conv.bias))
+                outs.append(ops.deconv2x2_lrelu(x[b], conv.weight, conv.bias, math=self.math))
             else:
-                outs.append(ops.conv1x1_lrelu(x[b], conv.weight, conv.bias, pool=self.pool))
+                outs.append(ops.conv1x1_lrelu(x[b], conv.weight, conv.bias, pool=self.pool, math=self.math))
         return outs[0].unsqueeze(0) if len(outs) == 1 else torch.stack(outs)
 
 

@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("URNN_B200_LIB", os.path.join(HERE, "liburnn_b200.so"))   # override: bring-up only
 
 URNN_CELL_ENCODER, URNN_CELL_DECODER = 0, 1
-MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
-MATH_BY_NAME = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}
+MATH_FP32, MATH_BF16 = 0, 2
+MATH_BY_NAME = {"fp32": MATH_FP32, "bf16": MATH_BF16}
 
 fp = C.c_void_p   # device pointers travel as integers
 
@@ -64,10 +64,10 @@ SIGNATURES = {
     "urnn_cgru_bwd_workspace_bytes": (sz, [C.POINTER(CellDesc)]),
     "urnn_cgru_bwd": (C.c_int, [C.POINTER(CellDesc), C.POINTER(CellParams), fp, fp, fp, fp, fp, fp, fp,
                                 C.POINTER(CellGrads), vp, sz, vp]),
-    "urnn_conv1x1_lrelu_fwd": (C.c_int, [i32, i32, i32, i32, i32, f32, fp, fp, fp, fp, vp]),
+    "urnn_conv1x1_lrelu_fwd": (C.c_int, [i32, i32, i32, i32, i32, f32, i32, fp, fp, fp, fp, vp]),
     "urnn_conv1x1_lrelu_bwd_workspace_bytes": (sz, [i32, i32, i32, i32, i32]),
     "urnn_conv1x1_lrelu_bwd": (C.c_int, [i32, i32, i32, i32, i32, f32, fp, fp, fp, fp, fp, fp, fp, vp, sz, vp]),
-    "urnn_deconv2x2_lrelu_fwd": (C.c_int, [i32, i32, i32, i32, f32, fp, fp, fp, fp, vp]),
+    "urnn_deconv2x2_lrelu_fwd": (C.c_int, [i32, i32, i32, i32, f32, i32, fp, fp, fp, fp, vp]),
     "urnn_deconv2x2_lrelu_bwd_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "urnn_deconv2x2_lrelu_bwd": (C.c_int, [i32, i32, i32, i32, f32, fp, fp, fp, fp, fp, fp, fp, vp, sz, vp]),
     "urnn_head_fwd_workspace_bytes": (sz, [i32, i32]),

@@ -20,7 +20,7 @@ _default_math = "fp32"
 
 
 def set_default_math(name):
-    """'fp32' (parity mode), 'tf32' or 'bf16' (tcgen05 modes) for modules that do not pin one."""
+    """'fp32' (parity mode) or 'bf16' (tcgen05 mode) for modules that do not pin one."""
     global _default_math
     if name not in _capi.MATH_BY_NAME:
         raise ValueError(f"unknown math mode {name!r}")
@@ -138,7 +138,7 @@ def cgru_cell(x, e, h, params, ksize, variant, math=None):
 
 
 # ---------------------------------------------------------------------------------------------- stems
-def conv1x1_lrelu_fwd(x, w, b, pool=1, slope=LRELU_SLOPE):
+def conv1x1_lrelu_fwd(x, w, b, pool=1, slope=LRELU_SLOPE, math=None):
     """[AvgPool2](LeakyReLU(conv1x1(x))) (reference utils.py:85-121).  x (Cin,H,W) -> (Cout,H/pool,W/pool)."""
     lib = _capi.load()
     x = _chk(x, "x")
@@ -146,18 +146,18 @@ def conv1x1_lrelu_fwd(x, w, b, pool=1, slope=LRELU_SLOPE):
     Cout = w.shape[0]
     w = _chk(w, "w", (Cout, Cin, 1, 1)); b = _chk(b, "b", (Cout,))
     y = torch.empty((Cout, H // pool, W // pool), dtype=torch.float32, device=x.device)
-    _capi.check(lib.urnn_conv1x1_lrelu_fwd(Cin, Cout, H, W, pool, slope, _p(x), _p(w), _p(b), _p(y), _stream()),
+    _capi.check(lib.urnn_conv1x1_lrelu_fwd(Cin, Cout, H, W, pool, slope, _math_code(math), _p(x), _p(w), _p(b), _p(y), _stream()),
                 "urnn_conv1x1_lrelu_fwd")
     return y
 
 
 class Conv1x1LreluFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, pool, slope):
+    def forward(ctx, x, w, b, pool, slope, math):
         ctx.cfg = (pool, slope)
         ctx.save_for_backward(x, w, b)
         with torch.no_grad():
-            return conv1x1_lrelu_fwd(x, w.detach(), b.detach(), pool, slope)
+            return conv1x1_lrelu_fwd(x, w.detach(), b.detach(), pool, slope, math)
 
     @staticmethod
     def backward(ctx, dy):
@@ -172,16 +172,16 @@ class Conv1x1LreluFn(torch.autograd.Function):
         ws = _ws(lib.urnn_conv1x1_lrelu_bwd_workspace_bytes(Cin, Cout, H, W, pool), x.device)
         _capi.check(lib.urnn_conv1x1_lrelu_bwd(Cin, Cout, H, W, pool, slope, _p(x), _p(w), _p(b), _p(dy), _p(dx),
                                                _p(dw), _p(db), _p(ws), ws.numel(), _stream()), "urnn_conv1x1_lrelu_bwd")
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
-def conv1x1_lrelu(x, w, b, pool=1, slope=LRELU_SLOPE):
+def conv1x1_lrelu(x, w, b, pool=1, slope=LRELU_SLOPE, math=None):
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
-        return Conv1x1LreluFn.apply(x, w, b, pool, slope)
-    return conv1x1_lrelu_fwd(x, w.detach(), b.detach(), pool, slope)
+        return Conv1x1LreluFn.apply(x, w, b, pool, slope, math)
+    return conv1x1_lrelu_fwd(x, w.detach(), b.detach(), pool, slope, math)
 
 
-def deconv2x2_lrelu_fwd(x, w, b, slope=LRELU_SLOPE):
+def deconv2x2_lrelu_fwd(x, w, b, slope=LRELU_SLOPE, math=None):
     """LeakyReLU(ConvTranspose2d(k=2,s=2)(x)) (reference utils.py:95-107).  x (Cin,H,W), w (Cin,Cout,2,2)."""
     lib = _capi.load()
     x = _chk(x, "x")
@@ -189,18 +189,18 @@ def deconv2x2_lrelu_fwd(x, w, b, slope=LRELU_SLOPE):
     Cout = w.shape[1]
     w = _chk(w, "w", (Cin, Cout, 2, 2)); b = _chk(b, "b", (Cout,))
     y = torch.empty((Cout, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
-    _capi.check(lib.urnn_deconv2x2_lrelu_fwd(Cin, Cout, H, W, slope, _p(x), _p(w), _p(b), _p(y), _stream()),
+    _capi.check(lib.urnn_deconv2x2_lrelu_fwd(Cin, Cout, H, W, slope, _math_code(math), _p(x), _p(w), _p(b), _p(y), _stream()),
                 "urnn_deconv2x2_lrelu_fwd")
     return y
 
 
 class Deconv2x2LreluFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, slope):
+    def forward(ctx, x, w, b, slope, math):
         ctx.slope = slope
         ctx.save_for_backward(x, w, b)
         with torch.no_grad():
-            return deconv2x2_lrelu_fwd(x, w.detach(), b.detach(), slope)
+            return deconv2x2_lrelu_fwd(x, w.detach(), b.detach(), slope, math)
 
     @staticmethod
     def backward(ctx, dy):
@@ -214,13 +214,13 @@ class Deconv2x2LreluFn(torch.autograd.Function):
         ws = _ws(lib.urnn_deconv2x2_lrelu_bwd_workspace_bytes(Cin, Cout, H, W), x.device)
         _capi.check(lib.urnn_deconv2x2_lrelu_bwd(Cin, Cout, H, W, ctx.slope, _p(x), _p(w), _p(b), _p(dy), _p(dx),
                                                  _p(dw), _p(db), _p(ws), ws.numel(), _stream()), "urnn_deconv2x2_lrelu_bwd")
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def deconv2x2_lrelu(x, w, b, slope=LRELU_SLOPE):
+def deconv2x2_lrelu(x, w, b, slope=LRELU_SLOPE, math=None):
     if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad or b.requires_grad):
-        return Deconv2x2LreluFn.apply(x, w, b, slope)
-    return deconv2x2_lrelu_fwd(x, w.detach(), b.detach(), slope)
+        return Deconv2x2LreluFn.apply(x, w, b, slope, math)
+    return deconv2x2_lrelu_fwd(x, w.detach(), b.detach(), slope, math)
 
 
 # ---------------------------------------------------------------------------------------------- head
