@@ -203,7 +203,27 @@ int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float
         return urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream);
     }
 #endif
-    // ---- encoder    // ---- head (flood_head.py:131-177)
+    // ---- encoder (encoder.py:187-215): stem conv (+pool) then ConvGRU, stage k feeds stage k+1
+    const float* cur = input; int cin = d->Cin;
+    for (int k = 0; k < 3; ++k) {
+        int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
+        URNN_TRY(urnn_conv1x1_lrelu_fwd(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, d->math, cur, p->enc_stem_w[k],
+                                        p->enc_stem_b[k], pl.s[k], stream));
+        URNN_TRY(urnn_cgru_fwd(&pl.enc[k], &p->enc_cell[k], pl.s[k], nullptr, sin[k], sout[k], pl.cell_ws,
+                               pl.cell_ws_bytes, stream));
+        cur = sout[k]; cin = d->enc_gru[k];
+    }
+    // ---- decoder (decoder.py:173-217): deepest first; x of the deepest stage is None -> zeros
+    URNN_TRY(urnn_cgru_fwd(&pl.dec[0], &p->dec_cell[0], nullptr, sout[2], sin[3], sout[3], pl.cell_ws, pl.cell_ws_bytes, stream));
+    URNN_TRY(urnn_deconv2x2_lrelu_fwd(d->dec_gru[0], d->dec_conv[0], pl.h[2], pl.w[2], sl, d->math, sout[3], p->dec_stem_w[0],
+                                      p->dec_stem_b[0], pl.up3, stream));
+    URNN_TRY(urnn_cgru_fwd(&pl.dec[1], &p->dec_cell[1], pl.up3, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, stream));
+    URNN_TRY(urnn_deconv2x2_lrelu_fwd(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, d->math, sout[4], p->dec_stem_w[1],
+                                      p->dec_stem_b[1], pl.up2, stream));
+    URNN_TRY(urnn_cgru_fwd(&pl.dec[2], &p->dec_cell[2], pl.up2, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, stream));
+    URNN_TRY(urnn_conv1x1_lrelu_fwd(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, d->math, sout[5], p->dec_stem_w[2], p->dec_stem_b[2],
+                                    pl.feat, stream));
+    // ---- head (flood_head.py:131-177)
     URNN_TRY(urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream));
     return URNN_OK;
 }
