@@ -23,45 +23,48 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     for (auto& v : hx) v = (rand() / (float)RAND_MAX) * 2 - 1;
     for (auto& v : hw) v = ((rand() / (float)RAND_MAX) * 2 - 1) * 0.2f;
     for (auto& v : hb) v = (rand() / (float)RAND_MAX) - 0.5f;
-    float *dx, *dw, *db, *dout, *dgam, *dbet, *dsc, *dsh; float2* dpart; double2* dtot; unsigned* dcnt;
+    float *dx, *dw, *db, *dgam, *dbet, *dsc, *dsh; __nv_bfloat16* dout; float2* dpart; double2* dtot; unsigned* dcnt;
     CK(cudaMalloc(&dx, hx.size() * 4)); CK(cudaMalloc(&dw, hw.size() * 4)); CK(cudaMalloc(&db, NOUT * 4));
-    CK(cudaMalloc(&dout, (size_t)NOUT * N * 4)); CK(cudaMalloc(&dgam, NOUT * 4)); CK(cudaMalloc(&dbet, NOUT * 4));
+    CK(cudaMalloc(&dout, (size_t)NOUT * N * 2)); CK(cudaMalloc(&dgam, NOUT * 4)); CK(cudaMalloc(&dbet, NOUT * 4));
     CK(cudaMalloc(&dsc, NOUT * 4)); CK(cudaMalloc(&dsh, NOUT * 4));
     CK(cudaMalloc(&dpart, 8 * 4096 * sizeof(float2))); CK(cudaMalloc(&dtot, 8 * sizeof(double2))); CK(cudaMalloc(&dcnt, 256));
-    CK(cudaMemset(dcnt, 0, 256)); CK(cudaMemset(dout, 0, (size_t)NOUT * N * 4));
+    CK(cudaMemset(dcnt, 0, 256)); CK(cudaMemset(dout, 0, (size_t)NOUT * N * 2));
     CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db, hb.data(), NOUT * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgam, hg.data(), NOUT * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dbet, hz.data(), NOUT * 4, cudaMemcpyHostToDevice));
-    unsigned* hdbg; CK(cudaHostAlloc(&hdbg, (148 * 16 + 6 * 64) * 4, cudaHostAllocMapped));
-    memset(hdbg, 0, (148 * 16 + 6 * 64) * 4);
+    unsigned* hdbg; CK(cudaHostAlloc(&hdbg, (148 * 16 + 7 * 64) * 4, cudaHostAllocMapped));
+    memset(hdbg, 0, (148 * 16 + 7 * 64) * 4);
     unsigned* ddbg; CK(cudaHostGetDevicePointer(&ddbg, hdbg, 0));
 
     std::vector<float> hgp((size_t)(K - c0) * 2 * N), hgs(2 * K, 0.7f), hgh(2 * K, 0.1f);
     for (auto& v : hgp) v = (rand() / (float)RAND_MAX) * 4 - 2;
-    float *dgp, *dgs, *dgh;
-    CK(cudaMalloc(&dgp, hgp.size() * 4)); CK(cudaMalloc(&dgs, hgs.size() * 4)); CK(cudaMalloc(&dgh, hgh.size() * 4));
-    CK(cudaMemcpy(dgp, hgp.data(), hgp.size() * 4, cudaMemcpyHostToDevice));
+    float *dgs, *dgh; __nv_bfloat16* dgp;
+    std::vector<__nv_bfloat16> hgpb(hgp.size());
+    for (size_t i = 0; i < hgp.size(); ++i) { hgpb[i] = __float2bfloat16(hgp[i]); hgp[i] = __bfloat162float(hgpb[i]); }
+    CK(cudaMalloc(&dgp, hgp.size() * 2)); CK(cudaMalloc(&dgs, hgs.size() * 4)); CK(cudaMalloc(&dgh, hgh.size() * 4));
+    CK(cudaMemcpy(dgp, hgpb.data(), hgp.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgs, hgs.data(), hgs.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgh, hgh.data(), hgh.size() * 4, cudaMemcpyHostToDevice));
-    tc::GemmParams P;
+    tc::GemmParams P; memset(&P, 0, sizeof(P));
     P.seg.src[0] = dx; P.seg.src[1] = dx + (size_t)c0 * N; P.seg.src[2] = dx + (size_t)(c0 + c1) * N;
     P.seg.cend[0] = c0; P.seg.cend[1] = c0 + c1; P.seg.cend[2] = K;
-    P.seg.vec = (N % 4 == 0); P.seg.plane = N; P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
+    P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = 0; P.seg.plane = N; P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
     const int gseg = (K - c0 - c1 > 0) ? 2 : 1; const int glen = (gseg == 2) ? K - c0 - c1 : c1; const int gk0 = K - glen;
     if (gated) { P.seg.gate_seg = gseg; P.seg.gate_ch0 = glen; P.seg.gate_pre = dgp; P.seg.gate_scale = dgs; P.seg.gate_shift = dgh; }
+    P.w_ks = 1; P.nrow1 = 1 << 30; P.nbias = NOUT; P.nout_store = NOUT; P.nstat = NOUT / 32;
     P.W = dw; P.w_ld = K; P.bias = db; P.NOUT = NOUT; P.K = K; P.N = N; P.out = dout; P.out_plane = N;
     int ntiles = (N + 127) / 128, grid = ntiles < 148 ? ntiles : 148;
     P.sink = StatSink{dpart, dtot, dcnt, NOUT / 32, 4096};
     P.aff = AffineOut{dsc, dsh, dgam, dbet, NOUT, 32, 32.0 * N, 1e-5f};
     int ns = 0; size_t smem = tc::gemm_smem_bytes(NOUT, K, &ns);
     P.nstage = ns; int cols = 32; while (cols < 2 * NOUT) cols <<= 1; P.tmem_cols = cols; P.dbg = ddbg;
-    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
-    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+    CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
     printf("grid=%d smem=%zu nstage=%d tmem_cols=%d\n", grid, smem, ns, cols); fflush(stdout);
     cudaEvent_t ev; CK(cudaEventCreate(&ev));
-    if (gated) tc::gemm_gn_kernel<true><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false><<<grid, tc::NTHREADS, smem>>>(P);
+    if (gated) tc::gemm_gn_kernel<true, 0><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false, 0><<<grid, tc::NTHREADS, smem>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev));
     auto t0 = std::chrono::steady_clock::now();
@@ -80,8 +83,9 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("kernel error: %s\n", cudaGetErrorString(e)); printf(" cta0:"); for (int i = 0; i < 15; ++i) printf(" %x", hdbg[i]); printf("\n"); return 2; }
-    std::vector<float> ho((size_t)NOUT * N);
-    CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<__nv_bfloat16> hob((size_t)NOUT * N); std::vector<float> ho((size_t)NOUT * N);
+    CK(cudaMemcpy(hob.data(), dout, hob.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < ho.size(); ++i) ho[i] = __bfloat162float(hob[i]);
     double maxerr = 0; long bad = 0;
     std::vector<float> xr(hx.size()), wr(hw.size());
     for (size_t i = 0; i < hx.size(); ++i) {
@@ -97,23 +101,23 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
             for (int k = 0; k < K; ++k) a += (double)wr[(size_t)n * K + k] * xr[(size_t)k * N + p];
             double d = fabs(a - ho[(size_t)n * N + p]);
             if (d > maxerr) maxerr = d;
-            if (d > 1e-3) { if (bad < 5) printf("  mismatch n=%d p=%d ref=%f got=%f\n", n, p, a, ho[(size_t)n * N + p]); ++bad; }
+            if (d > 1e-3 + 8e-3 * fabs(a)) { if (bad < 5) printf("  mismatch n=%d p=%d ref=%f got=%f\n", n, p, a, ho[(size_t)n * N + p]); ++bad; }
         }
     printf("max abs err %.3e, mismatches %ld -> %s\n", maxerr, bad, bad ? "FAIL" : "ok"); fflush(stdout);
-    if (N >= 60000) {
+    if (N >= 15000) {
         const unsigned* tr = hdbg + 148 * 16; unsigned t0 = tr[0];
-        printf("trace (us since setup done): kernel end %.1f\n", (tr[5 * 64] - t0) * 1e-3);
+        printf("trace (us since setup done): kernel entry %.1f kernel end %.1f\n", ((int)(tr[6 * 64] - t0)) * 1e-3, (tr[5 * 64] - t0) * 1e-3);
         for (int i = 0; i < 16; ++i)
             printf("  tile %2d: prod_done %7.1f  mma_issued %7.1f  epi_start %7.1f  epi_end %7.1f\n", i, (tr[64 + i] - t0) * 1e-3,
                    (tr[128 + i] - t0) * 1e-3, (tr[192 + i] - t0) * 1e-3, (tr[256 + i] - t0) * 1e-3);
         cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
         P.dbg = nullptr;
         CK(cudaEventRecord(a));
-        for (int i = 0; i < 10; ++i) { if (gated) tc::gemm_gn_kernel<true><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false><<<grid, tc::NTHREADS, smem>>>(P); }
+        for (int i = 0; i < 10; ++i) { if (gated) tc::gemm_gn_kernel<true, 0><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false, 0><<<grid, tc::NTHREADS, smem>>>(P); }
         CK(cudaEventRecord(b)); CK(cudaDeviceSynchronize());
         float ms; CK(cudaEventElapsedTime(&ms, a, b));
-        double us = ms * 100.0, bytes = ((double)K + NOUT) * N * 4;
-        printf("time %.1f us/launch, %.0f GB/s (in+out fp32)\n", us, bytes / us * 1e-3); fflush(stdout);
+        double us = ms * 100.0, bytes = ((double)K * 4 + NOUT * 2) * N;
+        printf("time %.1f us/launch, %.0f GB/s (fp32 in + bf16 out)\n", us, bytes / us * 1e-3); fflush(stdout);
     }
     return bad ? 1 : 0;
 }
@@ -127,6 +131,7 @@ int main() {
     rc |= run(64, 64, 128 * 5, 0, 0);
     rc |= run(192, 288, 128 * 300, 96, 96);
     rc |= run(96, 200, 15625, 8, 96);
+    rc |= run(192, 192, 15625, 0, 96);
     rc |= run(128, 224, 250000, 96, 64);
     return rc;
 }

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NOUT = P.NOUT, K = P.K, N = P.N;
+    if (P.dbg && blockIdx.x == 0 && tid == 0) { unsigned t_; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_)); P.dbg[148 * 16 + 6 * 64] = t_; }
     const int Kp = (K + 15) & ~15;                          // padded to the MMA K
     const int nkb = (Kp + KBLK - 1) / KBLK;                 // K blocks per tile
     const int last_k = Kp - (nkb - 1) * KBLK;               // valid (padded) channels in the last block
