@@ -228,3 +228,40 @@ def test_launches_are_counted():
         net(torch.rand(1, 1, 9, 16, 16, device=DEV), *st)
     torch.cuda.synchronize()
     assert lib.urnn_launch_count() - n0 == 6 * 3 + 6 + 4      # 6 cells x 3 kernels, 6 stems, 4 head sweeps
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sequence_runner_equals_step_loop(use_graph):
+    """SequenceRunner (ping-pong states, optional CUDA graph) == the reference-style per-step loop, bit for bit."""
+    from urnn_b200.runner import SequenceRunner
+    H, W, T = 32, 48, 5
+    net = build_ed(H, W, 9)
+    xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, 3)).to(DEV)
+    st = zero_states(H, W)
+    outs = []
+    with torch.no_grad():
+        for t in range(T):
+            out, *st = net(xs[t][None, None], *st)
+            outs.append(out[0, 0])
+    runner = SequenceRunner(net, H, W, 9, use_graph=use_graph)
+    depth, prob, final = runner.run(xs)
+    assert torch.equal(depth, torch.stack(outs))
+    for a, b in zip(final, st):
+        assert torch.equal(a, b[0])
+    depth2, _, _ = runner.run(xs)           # second run re-initialises the states
+    assert torch.equal(depth2, depth)
+
+
+def test_sequence_host_entry_point():
+    """urnn_ed_sequence_host (host buffers, overlapped copies) == the device-resident runner."""
+    from urnn_b200.runner import SequenceRunner
+    H, W = 24, 40
+    net = build_ed(H, W, 9)
+    for T in (1, 4, 7):
+        xs_host = torch.from_numpy(O.synthetic_event_inputs(H, W, T, 3)).pin_memory()
+        runner = SequenceRunner(net, H, W, 9, use_graph=False)
+        depth, _, final = runner.run(xs_host.to(DEV))
+        out_host, final_h = runner.run_host(xs_host)
+        assert torch.equal(out_host, depth.cpu())
+        for a, b in zip(final_h, final):
+            assert torch.equal(a, b)

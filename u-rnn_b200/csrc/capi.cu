@@ -228,10 +228,90 @@ int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float
     return URNN_OK;
 }
 
-size_t urnn_ed_sequence_host_workspace_bytes(const urnn_ed_desc*) { return 0; }
-int urnn_ed_sequence_host(const urnn_ed_desc*, const urnn_ed_params*, int32_t, const float*, float*, float* const*,
-                          void*, size_t, void*) {
-    set_error("ed_sequence_host: not implemented in this build"); return URNN_E_UNSUPPORTED;
+// ------------------------------------------------------------------------------------------------ host-buffer sequence
+// test.py:356-375 with host buffers: H2D of step t+1's input and D2H of step t-1's depth map overlap step t.
+struct SeqPlan {
+    float* in[2]; float* out[2]; float* st[2][6]; void* step_ws; size_t step_ws_bytes; size_t total;
+    size_t state_elems[6];
+};
+static int seq_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, SeqPlan* sp) {
+    EdPlan pl;
+    URNN_TRY(ed_plan(d, nullptr, 0, &pl));
+    const size_t N = (size_t)d->H * d->W;
+    const int ch[6] = {d->enc_gru[0], d->enc_gru[1], d->enc_gru[2], d->dec_gru[0], d->dec_gru[1], d->dec_gru[2]};
+    const int sc[6] = {0, 1, 2, 2, 1, 0};
+    Arena a(ws, ws_bytes);
+    for (int i = 0; i < 2; ++i) { sp->in[i] = a.take<float>((size_t)d->Cin * N); sp->out[i] = a.take<float>(2 * N); }
+    for (int k = 0; k < 6; ++k) {
+        sp->state_elems[k] = (size_t)ch[k] * (N >> (2 * sc[k]));
+        sp->st[0][k] = nullptr;                                   // ping buffer = the caller's state buffer
+        sp->st[1][k] = a.take<float>(sp->state_elems[k]);
+    }
+    sp->step_ws_bytes = pl.total;
+    sp->step_ws = a.take<char>(pl.total);
+    sp->total = align_up(a.off, 256);
+    return URNN_OK;
+}
+
+size_t urnn_ed_sequence_host_workspace_bytes(const urnn_ed_desc* d) {
+    SeqPlan sp;
+    if (seq_plan(d, nullptr, 0, &sp) != URNN_OK) return 0;
+    return sp.total;
+}
+
+int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T, const float* inputs_host,
+                          float* out_host, float* const* states, void* ws, size_t ws_bytes, void* stream) {
+    URNN_CHECK_ARG(d && p && inputs_host && out_host && states && T > 0, "ed_sequence_host: bad argument");
+    SeqPlan sp;
+    URNN_TRY(seq_plan(d, ws, ws_bytes, &sp));
+    if (sp.total > ws_bytes) { set_error("ed_sequence_host: workspace %zu < %zu bytes", ws_bytes, sp.total); return URNN_E_WORKSPACE; }
+    for (int k = 0; k < 6; ++k) { URNN_CHECK_ARG(states[k], "ed_sequence_host: null state %d", k); sp.st[0][k] = states[k]; }
+    // copy streams / events are created once per process (this entry point is the only one that owns CUDA objects)
+    static cudaStream_t s_in = nullptr, s_out = nullptr;
+    static cudaEvent_t ev_in[2], ev_step[2], ev_out[2], ev_free[2];
+    if (s_in == nullptr) {
+        URNN_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        URNN_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            URNN_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            URNN_CUDA(cudaEventCreateWithFlags(&ev_step[i], cudaEventDisableTiming));
+            URNN_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+            URNN_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)d->H * d->W, in_elems = (size_t)d->Cin * N;
+    // the copy streams must not run ahead of work already queued on the caller's stream
+    URNN_CUDA(cudaEventRecord(ev_free[0], st));
+    URNN_CUDA(cudaStreamWaitEvent(s_in, ev_free[0], 0));
+    URNN_CUDA(cudaStreamWaitEvent(s_out, ev_free[0], 0));
+    URNN_CUDA(cudaMemcpyAsync(sp.in[0], inputs_host, in_elems * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    URNN_CUDA(cudaEventRecord(ev_in[0], s_in));
+    for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        if (t + 1 < T) {                                    // prefetch the next input into the other buffer
+            if (t >= 1) URNN_CUDA(cudaStreamWaitEvent(s_in, ev_step[b ^ 1], 0));   // step t-1 has consumed it
+            URNN_CUDA(cudaMemcpyAsync(sp.in[b ^ 1], inputs_host + (size_t)(t + 1) * in_elems, in_elems * sizeof(float),
+                                      cudaMemcpyHostToDevice, s_in));
+            URNN_CUDA(cudaEventRecord(ev_in[b ^ 1], s_in));
+        }
+        URNN_CUDA(cudaStreamWaitEvent(st, ev_in[b], 0));
+        if (t >= 2) URNN_CUDA(cudaStreamWaitEvent(st, ev_out[b], 0));             // out[b] has been drained to the host
+        const float* sin[6]; float* sout[6];
+        for (int k = 0; k < 6; ++k) { sin[k] = sp.st[b][k]; sout[k] = sp.st[b ^ 1][k]; }
+        URNN_TRY(urnn_ed_step_fwd(d, p, sp.in[b], sin, sout, sp.out[b], sp.step_ws, sp.step_ws_bytes, stream));
+        URNN_CUDA(cudaEventRecord(ev_step[b], st));
+        URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
+        URNN_CUDA(cudaMemcpyAsync(out_host + (size_t)t * N, sp.out[b], N * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        URNN_CUDA(cudaEventRecord(ev_out[b], s_out));
+    }
+    if (T & 1) {                                            // final states live in the workspace buffers: copy back
+        for (int k = 0; k < 6; ++k)
+            URNN_CUDA(cudaMemcpyAsync(sp.st[0][k], sp.st[1][k], sp.state_elems[k] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    URNN_CUDA(cudaStreamSynchronize(s_out));
+    URNN_CUDA(cudaStreamSynchronize(st));
+    return URNN_OK;
 }
 
 }  // extern "C"
