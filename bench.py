@@ -2,14 +2,14 @@
 """
 bench.py -- grid-cells*steps/s of the U-RNN encoder-decoder time step (flood-depth forward) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math fp32|tf32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math bf16|fp32]
 
 One "step" = one ED time step (reference model.py:65-121) over the whole H x W grid.  Workload at N=1: the
 location1 full-resolution grid (500 x 500, 2 m / 1 min, historical_nums=30 => C_in=63), synthetic event,
 seeded random-init weights (no dataset / checkpoint offline).  Prints ONE JSON line.
 
   value     : cells*steps/s with the per-step inputs already resident in HBM (ring of distinct inputs)
-  e2e       : same metric through the public nn.Module API with HOST buffers: per step one H2D copy of the
+  e2e       : same metric through the C ABI with HOST buffers (urnn_ed_sequence_host): per step one H2D copy of the
               (C_in,H,W) input from pinned memory and one D2H copy of the (H,W) depth map, inside the timed region
   roofline  : dominant op timed alone with CUDA events (algorithmic bytes / time vs MEASURED_PEAKS.json hbm_gbs)
   cpu_baseline : the functional-torch port of the reference (oracle/torch_port.py) on this box's host cores
@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default=os.environ.get("URNN_MATH", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--math", default=os.environ.get("URNN_MATH", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--height", type=int, default=H_DEF)
     ap.add_argument("--width", type=int, default=W_DEF)
     ap.add_argument("--hist", type=int, default=HIST_DEF)
@@ -172,6 +172,7 @@ def run_reference_arm(a):
 # ---------------------------------------------------------------------------------------------- our arm
 def run_ours(a):
     from urnn_b200 import _capi, ops
+    from urnn_b200.runner import SequenceRunner
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -180,20 +181,25 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        raise NotImplementedError("spatially sharded multi-GPU step: not built yet")
     lib = _capi.load()
+    if world > 1:
+        # spatial sharding: every rank owns one H x W band of a (world*H) x W grid; the only per-step exchange is the
+        # in-kernel all-reduce of the normalisation statistics over NVLink peer memory (no NCCL on the data path)
+        import torch.distributed as dist
+        from urnn_b200 import dist as ud
+        dist.init_process_group("nccl", device_id=dev)
+        ud.init_spatial_sharding()
     ops.set_default_math(a.math)
     H, W, hist = a.height, a.width, a.hist
     C = 2 * hist + 3
     N = H * W
     net = build_net(H, W, C, a.math, dev)
+    runner = SequenceRunner(net, H, W, C, math=a.math, use_graph=False)
+    desc, params = runner.desc, net.ed_params()
     ring = 8
     xs_host = torch.from_numpy(synthetic_inputs(H, W, hist, ring)).pin_memory()
     xs_dev = xs_host.to(dev)
-    states0 = [torch.zeros(s, device=dev) for s in state_shapes(H, W)]
+    out = torch.empty((2, H, W), device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -201,43 +207,54 @@ def run_ours(a):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        st = list(states0)
-        with torch.no_grad():
-            for i in range(warmup):
-                st = fn(i, st)
-            barrier()
-            n0 = lib.urnn_launch_count()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def max_over_ranks(sec):
+        if dist is None:
+            return sec
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # (1) device-resident inputs: K steps of the whole encoder-decoder step, states ping-pong in HBM
+    def step(i):
+        ops.ed_step_fwd(desc, params, xs_dev[i % ring], runner.states[i & 1], runner.states[(i & 1) ^ 1], out, runner.ws)
+
+    with torch.no_grad():
+        for i in range(a.warmup):
+            step(i)
+        barrier()
+        n0 = lib.urnn_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
             e0.record()
-            for i in range(steps):
-                st = fn(i, st)
+            for i in range(a.steps):
+                step(i)
             e1.record()
             barrier()
-        return e0.elapsed_time(e1) * 1e-3, lib.urnn_launch_count() - n0
+        launches = lib.urnn_launch_count() - n0
+    sec = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    value = world * N * a.steps / sec
 
-    # (1) device-resident inputs
-    def step_resident(i, st):
-        out, *st = net(xs_dev[i % ring][None, None], *st)
-        return st
+    # (2) end to end through the C ABI with HOST buffers (urnn_ed_sequence_host): per step one H2D copy of the
+    #     (C_in,H,W) input from pinned memory and one D2H copy of the (H,W) depth map, overlapped with compute
+    chunk = min(a.steps, 16)
+    in_host = torch.empty((chunk, C, H, W), dtype=torch.float32).pin_memory()
+    for i in range(chunk):
+        in_host[i].copy_(xs_host[i % ring])
+    out_host = torch.empty((chunk, H, W), dtype=torch.float32).pin_memory()
+    runner.run_host(in_host[:max(1, min(a.warmup, chunk))], out_host[:max(1, min(a.warmup, chunk))])
+    barrier()
+    t0 = time.perf_counter()
+    done = 0
+    while done < a.steps:
+        n = min(chunk, a.steps - done)
+        runner.run_host(in_host[:n], out_host[:n], states=runner.states[0])
+        done += n
+    torch.cuda.synchronize()
+    sec_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e = world * N * a.steps / sec_e2e
 
-    with ClockSampler(local) as clk:
-        sec, launches = timed(step_resident, a.steps, a.warmup)
-    value = N * a.steps / sec
-
-    # (2) end to end: pinned host input -> device, step, depth map -> pinned host
-    out_host = torch.empty((1, 1, H, W), dtype=torch.float32).pin_memory()
-
-    def step_e2e(i, st):
-        x = xs_host[i % ring].to(dev, non_blocking=True)
-        out, *st = net(x[None, None], *st)
-        out_host.copy_(out, non_blocking=True)
-        return st
-
-    sec_e2e, _ = timed(step_e2e, a.steps, a.warmup)
-    e2e = N * a.steps / sec_e2e
-
-    # (3) roofline of the dominant op: the full-resolution decoder Skip-ConvGRU cell (36 % of step FLOPs)
+    # (3) roofline of the dominant op: the full-resolution decoder Skip-ConvGRU cell (36 % of the step's FLOPs and
+    #     its largest kernels); algorithmic bytes = (C_x + C_e + C_d + F) * 4 per cell
     cell = net.decoder.rnn1
     F, Cx = cell.num_features, cell.input_channels
     x = torch.rand(Cx, H, W, device=dev); e = torch.rand(F, H, W, device=dev)
@@ -246,40 +263,48 @@ def run_ours(a):
         for i in range(3):
             cell.step(x, e, hs[i % 4])
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 20
-        e0.record()
+        c0.record()
         for i in range(reps):
             cell.step(x, e, hs[i % 4])
-        e1.record()
+        c1.record()
         torch.cuda.synchronize()
-    cell_sec = e0.elapsed_time(e1) * 1e-3 / reps
+    cell_sec = c0.elapsed_time(c1) * 1e-3 / reps
     alg_bytes = (Cx + 2 * F + F) * 4 * N
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / cell_sec / 1e9
-    roofline = {"bound": "hbm", "kernel": f"decoder stage-1 Skip-ConvGRU cell step (in={Cx}, F={F}) at {H}x{W}, math={a.math}",
+    roofline = {"bound": "hbm", "kernel": f"decoder stage-1 Skip-ConvGRU cell step (in={Cx}, F={F}; 3 sweeps) at {H}x{W}, math={a.math}",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": cell_sec * 1e3}
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": cell_sec * 1e3,
+                "whole_step": {"algorithmic_bytes": (C + 2 * 188 + 160 + 1) * 4 * N,
+                               "achieved_GBps": (C + 2 * 188 + 160 + 1) * 4 * N * world * a.steps / sec / 1e9 / world,
+                               "frac": (C + 2 * 188 + 160 + 1) * 4 * N * a.steps / sec / 1e9 / peak}}
 
     # (4) CPU baseline beside it
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
-        v, s, cores = cpu_port_throughput(H, W, hist, 6, 2)
+        v, s_, cores = cpu_port_throughput(H, W, hist, 6, 2)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"6 ED steps at {H}x{W} after 2 warm-up ({s * 1e3:.0f} ms/step), torch {torch.__version__} CPU"}
+               "sample": f"6 ED steps at {H}x{W} after 2 warm-up ({s_ * 1e3:.0f} ms/step), torch {torch.__version__} CPU"}
 
     if rank == 0:
+        grid = f"{world * H}x{W} ({world} row bands of {H}x{W})" if world > 1 else f"{H}x{W}"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[a.math], "data": "synthetic",
-                "config": {"workload": f"location1 full-res {H}x{W}, C_in={C}, ED step forward (6 ConvGRU cells + stems + head)",
+                "dtype": {"fp32": "f32", "bf16": "bf16"}[a.math], "data": "synthetic",
+                "config": {"workload": f"location1 full-res {grid}, C_in={C}, ED step forward (6 ConvGRU cells + stems + head)",
                            "l2": "per-step working set ~600 MB (states in+out, inputs, LN affine) > 126 MB L2; inputs cycle through a ring of 8",
-                           "weights": "random init, torch.manual_seed(0)", "math": a.math},
+                           "weights": "random init, torch.manual_seed(0)", "math": a.math,
+                           "sharding": "row bands, in-kernel NVLink statistic all-reduce" if world > 1 else "none",
+                           "e2e_path": f"urnn_ed_sequence_host (C ABI, host buffers), {chunk}-step calls"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": C * N * 4, "d2h_bytes_per_step": N * 4,
                         "ms_per_step": sec_e2e / a.steps * 1e3},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line))
     if dist is not None:
+        from urnn_b200 import dist as ud
+        ud.shutdown_spatial_sharding()
         dist.destroy_process_group()
 
 

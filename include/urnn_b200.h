@@ -193,6 +193,24 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
                           const float* inputs_host, float* out_host, float* const* states,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Spatial sharding across the GPUs of one NVLink/NVSwitch box (one process per GPU).  The reference never shards
+ * the grid (its only parallelism is DDP over events, main.py:385-387); this is the B200 scaling axis of the path.
+ * Each rank owns a band of rows of every map (input, 6 states, head LayerNorm affine); weights are replicated.
+ * All ops are pixel-local for 1x1 filters except the GroupNorm / LayerNorm statistics (ConvRNN.py:97,103;
+ * head/network_blocks.py:94), which the kernels all-reduce inside their statistics epilogue through peer-mapped
+ * exchange buffers (CUDA IPC over NVLink; no NCCL call, no host round trip, CUDA-graph capturable).  Bands must
+ * have equal size (the element count of every normalisation is local count x world).
+ *   1. every rank: urnn_comm_local_init(world, rank, handle)  -> allocates its exchange buffer (~70 KB), returns
+ *      a 64-byte IPC handle;  2. all-gather the handles by any means (torch.distributed);  3. every rank:
+ *      urnn_comm_connect(all_handles).  From then on every statistics reduction of this process is global.
+ *      urnn_comm_destroy() returns to single-GPU behaviour.  These three calls synchronise / allocate. */
+#define URNN_COMM_HANDLE_BYTES 64
+int urnn_comm_local_init(int32_t world, int32_t rank, void* handle_out);
+int urnn_comm_connect(const void* all_handles);
+int urnn_comm_destroy(void);
+int urnn_comm_world(void);   /* 1 when no communicator is active */
+
 #ifdef __cplusplus
 }
 #endif

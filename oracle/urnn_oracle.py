@@ -22,6 +22,11 @@ error-budget run, float32 to mimic the reference's arithmetic width.
 """
 import numpy as np
 
+# Spatial-sharding model (tests only): when set, a callable that sums an array of local (sum, sumsq, count) triples
+# over all ranks (e.g. torch.distributed.all_reduce on gloo).  Statistics are the only cross-band quantity for 1x1
+# filters; everything else in this file is pixel-local or aligned to 4-row bands.
+STATS_ALLREDUCE = None
+
 GN_EPS = 1e-5      # torch.nn.GroupNorm default, ConvRNN.py:97,103
 LN_EPS = 1e-5      # torch.nn.LayerNorm default, head/network_blocks.py:94
 LRELU_SLOPE = 0.2  # utils.py:63, head/network_blocks.py:39
@@ -70,16 +75,27 @@ def group_norm(x, num_groups, gamma, beta, eps=GN_EPS, stats_from=None):
     c, h, w = x.shape
     g = x.reshape(num_groups, -1)
     gs = g if stats_from is None else stats_from.reshape(num_groups, -1)
-    mean = gs.mean(axis=1, keepdims=True)
-    var = ((gs - mean) ** 2).mean(axis=1, keepdims=True)
+    if STATS_ALLREDUCE is not None:
+        tri = np.stack([gs.sum(axis=1), (gs ** 2).sum(axis=1), np.full(num_groups, gs.shape[1], dtype=gs.dtype)])
+        tri = STATS_ALLREDUCE(tri.astype(np.float64))
+        mean = (tri[0] / tri[2])[:, None].astype(x.dtype)
+        var = (tri[1] / tri[2] - (tri[0] / tri[2]) ** 2)[:, None].astype(x.dtype)
+    else:
+        mean = gs.mean(axis=1, keepdims=True)
+        var = ((gs - mean) ** 2).mean(axis=1, keepdims=True)
     y = ((g - mean) / np.sqrt(var + x.dtype.type(eps))).reshape(c, h, w)
     return y * gamma[:, None, None] + beta[:, None, None]
 
 
 def layer_norm_chw(x, weight, bias, eps=LN_EPS):
     """nn.LayerNorm([C,H,W]) with per-element affine.  head/network_blocks.py:93-94."""
-    mean = x.mean()
-    var = ((x - mean) ** 2).mean()
+    if STATS_ALLREDUCE is not None:
+        tri = STATS_ALLREDUCE(np.array([[x.sum()], [(x ** 2).sum()], [x.size]], dtype=np.float64))
+        mean = x.dtype.type(tri[0, 0] / tri[2, 0])
+        var = x.dtype.type(tri[1, 0] / tri[2, 0] - (tri[0, 0] / tri[2, 0]) ** 2)
+    else:
+        mean = x.mean()
+        var = ((x - mean) ** 2).mean()
     return (x - mean) / np.sqrt(var + x.dtype.type(eps)) * weight + bias
 
 

@@ -1,0 +1,76 @@
+"""Multi-GPU (spatially sharded) == single-GPU, on real GPUs: two processes, one band each, statistics exchanged
+inside the kernels over peer-mapped buffers.  Skipped unless at least 2 CUDA devices are visible."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+H, W, HIST, T = 64, 48, 3, 3
+
+
+def _build(Hl, math):
+    from src.lib.model.networks.model import ED
+    from src.lib.model.networks.net_params import get_network_params
+    torch.manual_seed(0)
+    enc, dec = get_network_params(False, Hl, W, input_channels=2 * HIST + 3, math=math)
+    return ED(False, enc, dec, 0.5, False, input_height=Hl, input_width=W)
+
+
+def _worker(rank, world, port, tmp):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "u-rnn_b200")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import urnn_oracle as O
+    from urnn_b200 import dist as ud
+    ud.init_spatial_sharding()
+    dev = f"cuda:{rank}"
+    xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, HIST))
+    r0, rows = ud.band(H, world, rank)
+    errs = {}
+    for math in ("fp32", "bf16"):
+        full_sd = _build(H, math).state_dict()
+        net = _build(rows, math)
+        net.load_state_dict(ud.shard_state_dict(full_sd, world, rank), strict=True)
+        net = net.to(dev).eval()
+        st = [torch.zeros(1, *s.shape, device=dev) for s in O.zero_states(rows, W)]
+        outs = []
+        with torch.no_grad():
+            for t in range(T):
+                out, *st = net(xs[t][None, None, :, r0:r0 + rows].contiguous().to(dev), *st)
+                outs.append(out[0, 0].cpu().numpy())
+        ref = np.load(os.path.join(tmp, f"ref_{math}.npz"))
+        sc = [1, 2, 4, 4, 2, 1]
+        e = 0.0
+        for i, c in enumerate(sc):
+            e = max(e, float(np.abs(st[i].cpu().numpy()[0] - ref[f"state{i}"][:, r0 // c:(r0 + rows) // c]).max()))
+        errs[math] = e
+    np.save(os.path.join(tmp, f"err{rank}.npy"), np.array([errs["fp32"], errs["bf16"]]))
+    ud.shutdown_spatial_sharding()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_bands_equal_single_gpu(tmp_path):
+    from oracle import urnn_oracle as O
+    xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, HIST)).cuda()
+    for math in ("fp32", "bf16"):
+        net = _build(H, math).cuda().eval()
+        st = [torch.zeros(1, *s.shape, device="cuda") for s in O.zero_states(H, W)]
+        with torch.no_grad():
+            for t in range(T):
+                out, *st = net(xs[t][None, None], *st)
+        np.savez(tmp_path / f"ref_{math}.npz", **{f"state{i}": s.cpu().numpy()[0] for i, s in enumerate(st)})
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        e = np.load(tmp_path / f"err{r}.npy")
+        assert e[0] < 1e-5, e          # fp32: only the summation order of the statistics differs
+        assert e[1] < 2e-2, e          # bf16: rounding flips at bf16 boundaries, same bound as the single-GPU tests

@@ -34,6 +34,17 @@ static int check_cell(const urnn_cell_desc* d, const urnn_cell_params* p, const 
     return URNN_OK;
 }
 
+// ---- cross-GPU communicator (process-global: one process drives one GPU)
+static CommDev g_comm = {1, 0, {nullptr}, {nullptr}, nullptr};
+static void* g_comm_local = nullptr;
+static void* g_comm_peer[COMM_MAX_WORLD] = {nullptr};
+static const size_t kSlotBytes = (size_t)COMM_RING * COMM_MAX_WORLD * COMM_MAX_SETS * sizeof(double2);
+static const size_t kFlagBytes = (size_t)COMM_RING * COMM_MAX_WORLD * sizeof(unsigned);
+static const size_t kCommBytes = kSlotBytes + kFlagBytes + 256;
+
+void current_comm(CommDev* out) { *out = g_comm; }
+int comm_world() { return g_comm.world; }
+
 }  // namespace urnn
 
 using namespace urnn;
@@ -311,6 +322,59 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
     }
     URNN_CUDA(cudaStreamSynchronize(s_out));
     URNN_CUDA(cudaStreamSynchronize(st));
+    return URNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ communicator
+int urnn_comm_world(void) { return g_comm.world; }
+
+int urnn_comm_local_init(int32_t world, int32_t rank, void* handle_out) {
+    URNN_CHECK_ARG(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world && handle_out, "comm_local_init: bad argument");
+    URNN_CHECK_ARG(sizeof(cudaIpcMemHandle_t) <= URNN_COMM_HANDLE_BYTES, "comm_local_init: IPC handle larger than 64 bytes");
+    if (g_comm_local) urnn_comm_destroy();
+    URNN_CUDA(cudaMalloc(&g_comm_local, kCommBytes));
+    URNN_CUDA(cudaMemset(g_comm_local, 0, kCommBytes));
+    URNN_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    URNN_CUDA(cudaIpcGetMemHandle(&h, g_comm_local));
+    memset(handle_out, 0, URNN_COMM_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    g_comm.world = 1; g_comm.rank = rank;          // not active until urnn_comm_connect
+    g_comm_peer[rank] = g_comm_local;
+    g_comm.seq = (unsigned*)((char*)g_comm_local + kSlotBytes + kFlagBytes);
+    // remember the intended world in the (still inactive) communicator through the peer table size
+    for (int r = 0; r < COMM_MAX_WORLD; ++r) if (r != rank) g_comm_peer[r] = nullptr;
+    g_comm.slots[rank] = (double2*)g_comm_local;
+    g_comm.flags[rank] = (unsigned*)((char*)g_comm_local + kSlotBytes);
+    // world is stored negated until connected
+    g_comm.world = -world;
+    return URNN_OK;
+}
+
+int urnn_comm_connect(const void* all_handles) {
+    URNN_CHECK_ARG(all_handles && g_comm_local && g_comm.world < 0, "comm_connect: call urnn_comm_local_init first");
+    const int world = -g_comm.world, rank = g_comm.rank;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)all_handles + (size_t)r * URNN_COMM_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        URNN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        g_comm_peer[r] = ptr;
+        g_comm.slots[r] = (double2*)ptr;
+        g_comm.flags[r] = (unsigned*)((char*)ptr + kSlotBytes);
+    }
+    g_comm.world = world;
+    return URNN_OK;
+}
+
+int urnn_comm_destroy(void) {
+    cudaDeviceSynchronize();
+    const int world = g_comm.world < 0 ? -g_comm.world : g_comm.world;
+    for (int r = 0; r < world && r < COMM_MAX_WORLD; ++r)
+        if (r != g_comm.rank && g_comm_peer[r]) { cudaIpcCloseMemHandle(g_comm_peer[r]); g_comm_peer[r] = nullptr; }
+    if (g_comm_local) { cudaFree(g_comm_local); g_comm_local = nullptr; }
+    g_comm = CommDev{1, 0, {nullptr}, {nullptr}, nullptr};
     return URNN_OK;
 }
 

@@ -60,7 +60,7 @@ void tc_params_defaults(tc::GemmParams& P) {
     for (int i = 0; i < 3; ++i) { P.seg.src[i] = nullptr; P.seg.cend[i] = 0; P.seg.kind[i] = 0; }
     P.w_ks = 1; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0; P.bias = nullptr; P.nbias = 0;
     P.out = nullptr; P.out_f32 = nullptr; P.addend = nullptr; P.nstat = 0; P.slope = 0.f; P.img_w = 0; P.n_base = 0;
-    P.sink = StatSink{nullptr, nullptr, nullptr, 0, 0};
+    P.sink = StatSink{nullptr, nullptr, nullptr, 0, 0, CommDev{1, 0, {nullptr}, {nullptr}, nullptr}};
     P.aff = AffineOut{nullptr, nullptr, nullptr, nullptr, 0, 32, 1.0, 0.f};
     P.dbg = nullptr;
 }
@@ -189,8 +189,10 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     P.bias = p->b1; P.nbias = 2 * F;
     P.NOUT = split ? 3 * F : 2 * F; P.nout_store = P.NOUT;
     P.out = w.GP; P.nstat = 2 * F / 32;
-    P.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx};
-    P.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, 32.0 * (double)N, d->eps};
+    CommDev comm; current_comm(&comm);
+    const double gcount = 32.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);
+    P.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx, comm};
+    P.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, gcount, d->eps};
     URNN_TRY(tc_launch(P, tc::EPI_GN, st));
 
     // ---- sweep B
@@ -207,8 +209,8 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     }
     P.w_ld = Ktot; P.nrow1 = F; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0;
     P.bias = p->b2; P.nbias = F; P.NOUT = F; P.nout_store = F; P.out = w.C; P.nstat = F / 32;
-    P.sink = StatSink{w.partial2, w.total2, w.counter + 1, F / 32, w.gx};
-    P.aff = AffineOut{w.scale2, w.shift2, p->gn2_w, p->gn2_b, F, 32, 32.0 * (double)N, d->eps};
+    P.sink = StatSink{w.partial2, w.total2, w.counter + 1, F / 32, w.gx, comm};
+    P.aff = AffineOut{w.scale2, w.shift2, p->gn2_w, p->gn2_b, F, 32, gcount, d->eps};
     URNN_TRY(tc_launch(P, tc::EPI_GN, st));
 
     // ---- sweep C

@@ -69,13 +69,75 @@ __device__ __forceinline__ double warp_sum(double v) {
 // float2 partial per CTA into partial[set * stride + cta]; the last CTA to finish (ticket counter) sums the
 // partials of every set in a fixed order in double and writes total[set]; the result is therefore
 // run-to-run deterministic.  The counter resets itself so the same control block can be reused.
+// Spatial sharding (one process per GPU, the H x W grid split into row bands): normalisation statistics are the only
+// quantity exchanged per step.  Every rank owns an exchange buffer that its peers map through CUDA IPC; the last CTA of
+// a statistics-producing kernel stores its totals into slot `rank` of EVERY peer's buffer over NVLink, publishes a
+// flag (st.release.sys), waits for the flags of all ranks (ld.acquire.sys) and sums the slots in rank order, so all
+// ranks obtain bit-identical totals with one NVLink round trip and no host involvement (one-shot all-reduce).
+constexpr int COMM_MAX_WORLD = 8;
+constexpr int COMM_RING = 64;        // exchanges in flight are at most 1 apart between ranks; the ring avoids resets
+constexpr int COMM_MAX_SETS = 8;     // statistics sets per exchange (<= 8 GroupNorm groups / 2 LayerNorms)
+struct CommDev {
+    int world, rank;                               // world <= 1: no exchange
+    double2*  slots[COMM_MAX_WORLD];               // peer p: slots[p][(ring*world + src_rank)*COMM_MAX_SETS + set]
+    unsigned* flags[COMM_MAX_WORLD];               // peer p: flags[p][ring*world + src_rank] = epoch
+    unsigned* seq;                                 // local exchange counter (device memory)
+};
+
 struct StatSink {
     float2*   partial;   // [nsets][stride]
     double2*  total;     // [nsets]
     unsigned* counter;   // one ticket counter for this launch
     int       nsets;
     int       stride;    // >= number of CTAs contributing to a set
+    CommDev   comm;      // cross-GPU exchange of the totals (world <= 1: none)
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One-shot all-reduce of s.total[0..nsets) across ranks; called by all threads of the last CTA after the local
+// totals are written (and a __syncthreads()).  Deterministic: fixed summation order (rank 0, 1, ...).
+__device__ __forceinline__ void stats_exchange(const StatSink& s) {
+    const CommDev& c = s.comm;
+    if (c.world <= 1) return;
+    __shared__ unsigned sh_seq;
+    if (threadIdx.x == 0) sh_seq = *c.seq;
+    __syncthreads();
+    const unsigned seq = sh_seq, ring = seq % COMM_RING, epoch = seq / COMM_RING + 1;
+    const int slot0 = (int)(ring * c.world + c.rank) * COMM_MAX_SETS;
+    // 1. my totals -> slot `rank` of every rank (including myself)
+    for (int i = threadIdx.x; i < c.world * s.nsets; i += blockDim.x) {
+        const int peer = i / s.nsets, set = i % s.nsets;
+        c.slots[peer][slot0 + set] = s.total[set];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + ring * c.world + c.rank, epoch);
+    // 2. wait until every rank has published this exchange into MY buffer
+    if (threadIdx.x < c.world) {
+        const unsigned* f = c.flags[c.rank] + ring * c.world + threadIdx.x;
+        while (ld_acquire_sys(f) != epoch) { __nanosleep(64); }
+    }
+    __syncthreads();
+    // 3. sum in rank order
+    if (threadIdx.x < s.nsets) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < c.world; ++r) {
+            const volatile double2* src = c.slots[c.rank] + (int)(ring * c.world + r) * COMM_MAX_SETS + threadIdx.x;
+            a += src->x; b += src->y;
+        }
+        s.total[threadIdx.x] = make_double2(a, b);
+    }
+    if (threadIdx.x == 0) *c.seq = seq + 1;
+    __syncthreads();
+}
 
 // Called by ALL threads of the CTA after the CTA's partials are written and made visible.
 // ncontrib = CTAs contributing per set, ncta_total = CTAs in the launch.  Optionally the last CTA also
@@ -116,6 +178,7 @@ __device__ __forceinline__ void stats_finalize_last_cta(const StatSink& s, int n
         }
         __syncthreads();
     }
+    stats_exchange(s);
     if (aff != nullptr) {
         __threadfence();
         for (int c = threadIdx.x; c < aff->channels; c += blockDim.x) {

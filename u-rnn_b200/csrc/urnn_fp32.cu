@@ -126,12 +126,14 @@ int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
 
     GnStatsEpilogue ep1;
     ep1.bias = p->b1; ep1.out = w.G; ep1.plane = N; ep1.vec = (N % 4 == 0);
-    ep1.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx};
-    ep1.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, 32.0 * (double)N, d->eps};
+    CommDev comm; current_comm(&comm);
+    const double gcount = 32.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);
+    ep1.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx, comm};
+    ep1.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, gcount, d->eps};
     GnStatsEpilogue ep2;
     ep2.bias = p->b2; ep2.out = w.C; ep2.plane = N; ep2.vec = (N % 4 == 0);
-    ep2.sink = StatSink{w.partial2, w.total2, w.counter + 1, F / 32, w.gx};
-    ep2.aff = AffineOut{w.scale2, w.shift2, p->gn2_w, p->gn2_b, F, 32, 32.0 * (double)N, d->eps};
+    ep2.sink = StatSink{w.partial2, w.total2, w.counter + 1, F / 32, w.gx, comm};
+    ep2.aff = AffineOut{w.scale2, w.shift2, p->gn2_w, p->gn2_b, F, 32, gcount, d->eps};
     AView A1{p->w1 + aoff, (long)Ktot * kk, 1};
     AView A2{p->w2 + aoff, (long)Ktot * kk, 1};
 
@@ -204,8 +206,9 @@ int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, cons
     long N = (long)H * W;
     HeadDev hd;
     hd.p = *p; hd.cls_thred = cls_thred; hd.eps = ln_eps; hd.slope = slope; hd.plane = N;
-    hd.count = 16.0 * (double)N;
-    hd.sink = StatSink{w.partial, w.total, w.counter, 5, w.gx};
+    CommDev comm; current_comm(&comm);
+    hd.count = 16.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);
+    hd.sink = StatSink{w.partial, w.total, w.counter, 5, w.gx, comm};
     head_kernel<0><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
     head_kernel<1><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
     head_kernel<2><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();

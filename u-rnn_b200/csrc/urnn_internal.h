@@ -6,6 +6,10 @@
 
 namespace urnn {
 
+struct CommDev;
+void current_comm(CommDev* out);      // the active cross-GPU communicator (world = 1 when none)
+int comm_world();
+
 // per-cell workspace view shared by the fp32 and tcgen05 paths
 struct CellWsView {
     float *G, *C, *scale1, *shift1, *scale2, *shift2;   // pre-GN gate / candidate maps, folded GN affines

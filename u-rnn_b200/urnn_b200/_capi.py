@@ -81,6 +81,10 @@ SIGNATURES = {
     "urnn_ed_sequence_host_workspace_bytes": (sz, [C.POINTER(EdDesc)]),
     "urnn_ed_sequence_host": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), i32, vp, vp, C.POINTER(fp),
                                         vp, sz, vp]),
+    "urnn_comm_local_init": (C.c_int, [i32, i32, vp]),
+    "urnn_comm_connect": (C.c_int, [vp]),
+    "urnn_comm_destroy": (C.c_int, []),
+    "urnn_comm_world": (C.c_int, []),
 }
 
 _lib = None
