@@ -104,3 +104,20 @@ def test_argument_validation_without_gpu():
     ed.H, ed.W, ed.Cin = 30, 32, 9
     assert lib.urnn_ed_step_workspace_bytes(ctypes.byref(ed)) == 0
     assert b"multiples of 4" in lib.urnn_last_error()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code"), reason="reference tree only exists in the build container")
+def test_overlay_resolution_with_reference_tree():
+    """With [u-rnn_b200, reference/code] on sys.path the hot-path modules are ours and the rest is the reference's."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.dont_write_bytecode=True; sys.path[:0]=[%r, '/root/reference/code'];"
+        "import src.lib.model.networks.model as m, src.lib.model.networks.losses as l, src.lib.utils.net_config as n,"
+        " src.lib.model.earlystopping as e, src.lib.model.networks.ConvRNN as c;"
+        "print(m.__file__); print(c.__file__); print(l.__file__); print(n.__file__); print(e.__file__)"
+    ) % os.path.join(root, "u-rnn_b200")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout.split()
+    assert "u-rnn_b200" in out[0] and "u-rnn_b200" in out[1]
+    assert out[2].startswith("/root/reference") and out[3].startswith("/root/reference") and out[4].startswith("/root/reference")

@@ -23,7 +23,16 @@ static int tc_launch_t(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st
         URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<GATED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
         attr_set = true;
     }
-    tc::gemm_gn_kernel<GATED, EPI><<<grid, tc::NTHREADS, smem, st>>>(P);
+    // Programmatic dependent launch: the next kernel's CTAs may start their prologue (barrier init, TMEM allocation,
+    // weight conversion) while the previous kernel drains; they touch its outputs only after griddepcontrol.wait.
+    static const bool pdl = !(getenv("URNN_PDL") && getenv("URNN_PDL")[0] == '0');
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    URNN_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_gn_kernel<GATED, EPI>, (const tc::GemmParams)P));
     URNN_LAUNCH_CHECK();
     return URNN_OK;
 }
@@ -106,6 +115,8 @@ cgru_blend_bf16_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16*
                        const float* __restrict__ h, const float* __restrict__ sc1, const float* __restrict__ sh1,
                        const float* __restrict__ sc2, const float* __restrict__ sh2, float* __restrict__ h_out,
                        long N, long nquad) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nquad) return;
     const uint2 gw = __ldg(reinterpret_cast<const uint2*>(G) + idx);
@@ -215,8 +226,18 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
 
     // ---- sweep C
     const long nquad = (long)F * N / 4;
-    cgru_blend_bf16_kernel<<<(unsigned)((nquad + 255) / 256), 256, 0, st>>>(w.GP, w.C, h, w.scale1, w.shift1, w.scale2,
-                                                                            w.shift2, h_out, N, nquad);
+    {
+        static const bool pdl = !(getenv("URNN_PDL") && getenv("URNN_PDL")[0] == '0');
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((nquad + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+        URNN_CUDA(cudaLaunchKernelEx(&cfg, cgru_blend_bf16_kernel, (const __nv_bfloat16*)w.GP, (const __nv_bfloat16*)w.C, h,
+                                     (const float*)w.scale1, (const float*)w.shift1, (const float*)w.scale2,
+                                     (const float*)w.shift2, h_out, N, nquad));
+    }
     URNN_LAUNCH_CHECK();
     return URNN_OK;
 }

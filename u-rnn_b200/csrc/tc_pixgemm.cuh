@@ -33,6 +33,7 @@ constexpr int NEPI = 256;             // epilogue threads: warp w owns TMEM lane
 constexpr int NTHREADS = NEPI + NPROD + 32;
 constexpr int MMA_WARP = (NEPI + NPROD) / 32;
 constexpr int MAXG = 8;               // NOUT <= 256 -> at most 8 groups of 32 output channels
+constexpr int MAXKB = 5;              // K <= 320 channels per contraction
 constexpr size_t SMEM_CAP = 229376;   // dynamic shared memory budget (227 KB opt-in limit minus static use)
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -232,13 +233,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const uint32_t a_off = w_off + (uint32_t)nkb * wblk_bytes;
     const uint32_t bias_off = a_off + (uint32_t)P.nstage * STAGE_BYTES;
     const uint32_t bar_off = bias_off + 1024;
+    const uint32_t tab_off = bar_off + 512;                  // per-channel source table: MAXKB*64 entries of 32 bytes
     // barriers: full[nstage], empty[nstage], tmem_full[2], tmem_empty[2]
     const uint32_t full0 = base + bar_off, empty0 = full0 + 8 * P.nstage;
     const uint32_t tfull0 = empty0 + 8 * P.nstage, tempty0 = tfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + bar_off + 16 * P.nstage + 32);
     float* sbias = reinterpret_cast<float*>(sm + bias_off);
+    struct ChanEnt { const char* ptr; const char* gptr; float sc, sh; int meta; int pad; };   // meta: 1 valid, 2 bf16, 4 gated
+    ChanEnt* ctab = reinterpret_cast<ChanEnt*>(sm + tab_off);
     __shared__ float red[2][4][MAXG];   // [sum|sumsq][lane quarter][group]; each (quarter, group) has one owner warp
 
+    // allow the next kernel in the stream to begin its own prologue as soon as SMs free up (PDL)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
     if (tid == 0) {
         for (int s = 0; s < P.nstage; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
@@ -266,11 +272,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             *reinterpret_cast<uint4*>(sm + w_off + kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
         }
     }
+    // where every reduction channel lives: plane base pointer, dtype, optional reset-gate map and folded GN affine
+    // (gate_scale / gate_shift are outputs of the previous kernel: read them only after the dependency wait)
+    for (int k = tid; k < nkb * KBLK; k += NTHREADS) {
+        ChanEnt e; e.ptr = nullptr; e.gptr = nullptr; e.sc = 0.f; e.sh = 0.f; e.meta = 0; e.pad = 0;
+        if (k < K) {
+            const Segs& S = P.seg;
+            const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
+            const int cc = k - (sg == 0 ? 0 : S.cend[sg - 1]);
+            e.ptr = reinterpret_cast<const char*>(S.src[sg]) + (long)cc * S.plane * (S.kind[sg] ? 2 : 4);
+            e.meta = 1 | (S.kind[sg] ? 2 : 0);
+            if (GATED && sg == S.gate_seg) {
+                e.gptr = reinterpret_cast<const char*>(S.gate_pre) + (long)(S.gate_ch0 + cc) * S.plane * 2;
+                e.meta |= 4 | ((S.gate_ch0 + cc) << 8);
+            }
+        }
+        ctab[k] = e;
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above reads only parameters; from here on the previous kernel's outputs are consumed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if constexpr (GATED) {
+        for (int k = tid; k < nkb * KBLK; k += NTHREADS) {
+            const int m = ctab[k].meta;
+            if (m & 4) { ctab[k].sc = __ldg(P.seg.gate_scale + (m >> 8)); ctab[k].sh = __ldg(P.seg.gate_shift + (m >> 8)); }
+        }
+        __syncthreads();
+    }
 #define TC_DBG(slot, val) do { if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 16 + (slot)] = (val); } while (0)
 #define TC_TRACE(role, idx) do { if (P.dbg && blockIdx.x == 0 && (tid & 31) == 0 && (idx) < 64) { unsigned t_; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_)); P.dbg[148 * 16 + (role) * 64 + (idx)] = t_; } } while (0)
     TC_DBG(0, 0x100u | tmem_base);
@@ -285,37 +317,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         // j = (pixel%64)/8 stored at chunk position j ^ (k&7).  Units (tile, K block) are streamed two deep.
         const int pt = tid - NEPI;
         const Segs& S = P.seg;
-        struct Buf { float v[2][8]; float g[GATED ? 2 : 1][8]; int gch[2]; };
+        const int ch0 = pt >> 4, px8 = pt & 15;               // chunk c handles channel-in-block ch0 + 32c, pixels px8*8..+7
         int trace_i = 0;
-
-        auto issue = [&](int tile, int kb, Buf& b) {
-            const int kvalid = (kb == nkb - 1) ? last_k : KBLK;      // channels of this block the MMA will read
+        // the unit loop only reads its channel's entry of the shared source table and adds the tile offset (no
+        // segment decode, no 64-bit multiplies, no per-element branches)
+        bool aligned = (N & 3) == 0;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const int idx = pt + c * NPROD;
-                const int ch = idx >> 4, px = (idx & 15) * 8;
-                const int k = kb * KBLK + ch;
-                const long p = (long)tile * TILE_M + px;
-                b.gch[c] = -1;
-                if (ch < kvalid && k < K && p < N) {
-                    const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
-                    const int cc = k - (sg == 0 ? 0 : S.cend[sg - 1]);
-                    const int nvalid = (N - p >= 8) ? 8 : (int)(N - p);
-                    if constexpr (EPI == EPI_POOL) {
-                        load8_quads(reinterpret_cast<const float*>(S.src[sg]) + (long)cc * S.plane, p >> 2, (long)N >> 2,
-                                    P.img_w >> 1, P.img_w, b.v[c]);
-                    } else {
-                        load8(S.src[sg], S.kind[sg], (long)cc * S.plane + p, nvalid, b.v[c]);
-                    }
-                    if constexpr (GATED) {
-                        if (sg == S.gate_seg) {
-                            b.gch[c] = S.gate_ch0 + cc;
-                            load8(S.gate_pre, 1, (long)b.gch[c] * S.plane + p, nvalid, b.g[c]);
-                        }
-                    }
+        for (int i = 0; i < 3; ++i)
+            aligned = aligned && ((reinterpret_cast<uintptr_t>(S.src[i]) & (S.kind[i] ? 7 : 15)) == 0);
+        if (GATED) aligned = aligned && ((reinterpret_cast<uintptr_t>(S.gate_pre) & 7) == 0);
+        const uint32_t soff0 = (uint32_t)((px8 >> 3) * 8192 + (ch0 >> 3) * 1024 + (ch0 & 7) * 128 + (((px8 & 7) ^ (ch0 & 7)) << 4));
+        const uint32_t soff1 = soff0 + 4 * 1024;             // chunk 1 = channel ch0 + 32: four K atoms further
+        struct Buf { float v[2][8]; float g[GATED ? 2 : 1][8]; float sc[2], sh[2]; int meta[2]; };
+
+        auto ld8 = [&](const char* ptr, bool bf16, long tile, bool whole, int nvalid, float (&v)[8]) {
+            if (!bf16) {
+                const float* s = reinterpret_cast<const float*>(ptr) + tile * TILE_M + px8 * 8;
+                if (whole) {
+                    const float4 lo = __ldg(reinterpret_cast<const float4*>(s));
+                    const float4 hi = __ldg(reinterpret_cast<const float4*>(s) + 1);
+                    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
                 } else {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) b.v[c][u] = 0.f;
+                    for (int u = 0; u < 8; ++u) v[u] = (u < nvalid) ? __ldg(s + u) : 0.f;
+                }
+            } else {
+                const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(ptr) + tile * TILE_M + px8 * 8;
+                if (whole) {
+                    const uint2 w0 = __ldg(reinterpret_cast<const uint2*>(s));
+                    const uint2 w1 = __ldg(reinterpret_cast<const uint2*>(s) + 1);
+                    unpack_bf16x2(w0.x, v[0], v[1]); unpack_bf16x2(w0.y, v[2], v[3]);
+                    unpack_bf16x2(w1.x, v[4], v[5]); unpack_bf16x2(w1.y, v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = (u < nvalid) ? __bfloat162float(s[u]) : 0.f;
+                }
+            }
+        };
+        auto issue = [&](int tile, int kb, Buf& b) {
+            const long p = (long)tile * TILE_M + px8 * 8;
+            const int nvalid = (p >= N) ? 0 : ((N - p >= 8) ? 8 : (int)(N - p));
+            const bool whole = aligned && nvalid == 8;
+#pragma unroll
+            const int kvalid = (kb == nkb - 1) ? last_k : KBLK;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const ChanEnt e = ctab[kb * KBLK + ch0 + 32 * c];
+                b.meta[c] = (nvalid > 0 && ch0 + 32 * c < kvalid) ? e.meta : 0;
+                if (b.meta[c] & 1) {
+                    if constexpr (EPI == EPI_POOL) {
+                        load8_quads(reinterpret_cast<const float*>(e.ptr), p >> 2, (long)N >> 2, P.img_w >> 1, P.img_w, b.v[c]);
+                    } else {
+                        ld8(e.ptr, (e.meta & 2) != 0, tile, whole, nvalid, b.v[c]);
+                    }
+                    if constexpr (GATED) {
+                        if (e.meta & 4) { ld8(e.gptr, true, tile, whole, nvalid, b.g[c]); b.sc[c] = e.sc; b.sh[c] = e.sh; }
+                    }
                 }
             }
         };
@@ -324,20 +381,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             const int kvalid = (kb == nkb - 1) ? last_k : KBLK;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const int idx = pt + c * NPROD;
-                const int ch = idx >> 4, px8 = idx & 15;
-                if (ch < kvalid) {
-                    if constexpr (GATED) {
-                        if (b.gch[c] >= 0) {
-                            const float sc = __ldg(S.gate_scale + b.gch[c]), sh = __ldg(S.gate_shift + b.gch[c]);
+                if (ch0 + 32 * c < kvalid) {
+                    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                    if (b.meta[c] & 1) {
+                        if constexpr (GATED) {
+                            if (b.meta[c] & 4) {
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) b.v[c][u] *= sigmoid_fast(fmaf(b.g[c][u], sc, sh));
+                                for (int u = 0; u < 8; ++u) b.v[c][u] *= sigmoid_fast(fmaf(b.g[c][u], b.sc[c], b.sh[c]));
+                            }
                         }
+                        pk = make_uint4(pack_bf16(b.v[c][0], b.v[c][1]), pack_bf16(b.v[c][2], b.v[c][3]),
+                                        pack_bf16(b.v[c][4], b.v[c][5]), pack_bf16(b.v[c][6], b.v[c][7]));
                     }
-                    uint4 pk = make_uint4(pack_bf16(b.v[c][0], b.v[c][1]), pack_bf16(b.v[c][2], b.v[c][3]),
-                                          pack_bf16(b.v[c][4], b.v[c][5]), pack_bf16(b.v[c][6], b.v[c][7]));
-                    const int kk = ch & 7;
-                    *reinterpret_cast<uint4*>(st + (px8 >> 3) * 8192 + (ch >> 3) * 1024 + kk * 128 + (((px8 & 7) ^ kk) << 4)) = pk;
+                    *reinterpret_cast<uint4*>(st + (c ? soff1 : soff0)) = pk;
                 }
             }
             fence_proxy_async();                             // generic-proxy stores -> visible to tcgen05.mma
@@ -415,6 +471,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             const bool valid = p < N;
             const float vmask = valid ? 1.f : 0.f;
             const long pc = valid ? p : 0;
+            // the addend map (r-independent candidate part) does not depend on this tile's MMA: fetch it first
+            float adv[1][EPI == EPI_GN ? 32 : 1];
+            if constexpr (EPI == EPI_GN) {
+                if (P.addend != nullptr) {
+#pragma unroll
+                    for (int gi = 0; gi < MAXG / 2; ++gi) {
+                        const int g = ghalf + 2 * gi;
+                        if (g < ng && gi < 1) {
+                            const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) adv[gi][i] = __bfloat162float(ad[(long)i * P.out_plane]);
+                        }
+                    }
+                }
+            }
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             if (warp == 0) TC_TRACE(3, (tile - (int)blockIdx.x) / (int)gridDim.x);
@@ -430,9 +501,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                         __nv_bfloat16* o = P.out + (long)(g * 32) * P.out_plane + pc;
                         const float* bs = sbias + g * 32;
                         if (P.addend != nullptr) {
-                            const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
+                            if (gi < 1) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(ad[(long)i * P.out_plane]);
+                                for (int i = 0; i < 32; ++i) v[i] += adv[0][i];
+                            } else {
+                                const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(ad[(long)i * P.out_plane]);
+                            }
                         }
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
@@ -518,9 +594,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
 // dynamic shared memory needed for a given problem; 0 if it cannot fit
 static inline size_t gemm_smem_bytes(int NOUT, int K, int* nstage_out) {
     const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
-    const size_t fixed = 1024 /*align slack*/ + (size_t)nkb * NOUT * 128 + 1024 /*bias*/ + 512 /*barriers*/;
+    const size_t fixed = 1024 /*align slack*/ + (size_t)nkb * NOUT * 128 + 1024 /*bias*/ + 512 /*barriers*/ + (size_t)nkb * KBLK * 32 /*source table*/;
     const size_t cap = SMEM_CAP;
-    if (fixed + 2 * STAGE_BYTES > cap) return 0;
+    if (fixed + 2 * STAGE_BYTES > cap || nkb > MAXKB) return 0;
     int ns = (int)((cap - fixed) / STAGE_BYTES);
     if (ns > 8) ns = 8;
     if (nstage_out) *nstage_out = ns;
