@@ -15,7 +15,7 @@ def cgru_cell(p, prefix, x, hidden, module, nf):
     """CGRU_cell.forward, one step (reference ConvRNN.py:140-190).  x (B,C,H,W) | None, hidden (B,F|2F,H,W)."""
     if x is None:
         cin = p[prefix + "conv1.0.weight"].shape[1] - hidden.shape[1]
-        x = torch.zeros(hidden.size(0), cin, hidden.size(2), hidden.size(3))
+        x = torch.zeros(hidden.size(0), cin, hidden.size(2), hidden.size(3), dtype=hidden.dtype)
     pad = (p[prefix + "conv1.0.weight"].shape[-1] - 1) // 2
     combined_1 = torch.cat((x, hidden), 1)
     gates = F.conv2d(combined_1, p[prefix + "conv1.0.weight"], p[prefix + "conv1.0.bias"], 1, pad)

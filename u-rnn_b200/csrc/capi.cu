@@ -73,10 +73,16 @@ int urnn_cgru_fwd(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     }
 }
 
-size_t urnn_cgru_bwd_workspace_bytes(const urnn_cell_desc*) { return 0; }
-int urnn_cgru_bwd(const urnn_cell_desc*, const urnn_cell_params*, const float*, const float*, const float*,
-                  const float*, float*, float*, float*, const urnn_cell_grads*, void*, size_t, void*) {
-    set_error("cgru_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+size_t urnn_cgru_bwd_workspace_bytes(const urnn_cell_desc* d) {
+    if (!d || d->F <= 0 || d->F % 32) return 0;
+    return cgru_bwd_workspace(d);
+}
+int urnn_cgru_bwd(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e, const float* h,
+                  const float* dh_out, float* dx, float* de, float* dh, const urnn_cell_grads* grads, void* ws,
+                  size_t ws_bytes, void* stream) {
+    URNN_TRY(check_cell(d, p, e, h, dh_out ? (const float*)dh_out : nullptr));
+    URNN_CHECK_ARG(dh_out, "cgru_bwd: null dh_out");
+    return cgru_bwd_fp32(d, p, x, e, h, dh_out, dx, de, dh, grads, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool, float slope, int32_t math,
@@ -92,10 +98,17 @@ int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int3
 #endif
     return conv1x1_lrelu_fwd_fp32(Cin, Cout, H, W, pool, slope, x, w, b, y, (cudaStream_t)stream);
 }
-size_t urnn_conv1x1_lrelu_bwd_workspace_bytes(int32_t, int32_t, int32_t, int32_t, int32_t) { return 0; }
-int urnn_conv1x1_lrelu_bwd(int32_t, int32_t, int32_t, int32_t, int32_t, float, const float*, const float*,
-                           const float*, const float*, float*, float*, float*, void*, size_t, void*) {
-    set_error("conv1x1_lrelu_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+size_t urnn_conv1x1_lrelu_bwd_workspace_bytes(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool) {
+    return conv1x1_lrelu_bwd_workspace(Cin, Cout, H, W, pool);
+}
+int urnn_conv1x1_lrelu_bwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool, float slope, const float* x,
+                           const float* w, const float* b, const float* dy, float* dx, float* dw, float* db, void* ws,
+                           size_t ws_bytes, void* stream) {
+    URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0 && (pool == 1 || pool == 2), "conv1x1_lrelu_bwd: bad shape");
+    URNN_CHECK_ARG(pool == 1 || (H % 2 == 0 && W % 2 == 0), "conv1x1_lrelu_bwd: AvgPool2 needs even H, W");
+    URNN_CHECK_ARG(x && w && b && dy && ws, "conv1x1_lrelu_bwd: null pointer");
+    URNN_CHECK_ARG((dw == nullptr) == (db == nullptr), "conv1x1_lrelu_bwd: dw and db must be given together");
+    return conv1x1_lrelu_bwd_fp32(Cin, Cout, H, W, pool, slope, x, w, b, dy, dx, dw, db, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope, int32_t math, const float* x,
@@ -109,10 +122,16 @@ int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, fl
 #endif
     return deconv2x2_lrelu_fwd_fp32(Cin, Cout, H, W, slope, x, w, b, y, (cudaStream_t)stream);
 }
-size_t urnn_deconv2x2_lrelu_bwd_workspace_bytes(int32_t, int32_t, int32_t, int32_t) { return 0; }
-int urnn_deconv2x2_lrelu_bwd(int32_t, int32_t, int32_t, int32_t, float, const float*, const float*, const float*,
-                             const float*, float*, float*, float*, void*, size_t, void*) {
-    set_error("deconv2x2_lrelu_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+size_t urnn_deconv2x2_lrelu_bwd_workspace_bytes(int32_t Cin, int32_t Cout, int32_t H, int32_t W) {
+    return deconv2x2_lrelu_bwd_workspace(Cin, Cout, H, W);
+}
+int urnn_deconv2x2_lrelu_bwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, float slope, const float* x, const float* w,
+                             const float* b, const float* dy, float* dx, float* dw, float* db, void* ws, size_t ws_bytes,
+                             void* stream) {
+    URNN_CHECK_ARG(Cin > 0 && Cout > 0 && H > 0 && W > 0, "deconv2x2_lrelu_bwd: bad shape");
+    URNN_CHECK_ARG(x && w && b && dy && ws, "deconv2x2_lrelu_bwd: null pointer");
+    URNN_CHECK_ARG((dw == nullptr) == (db == nullptr), "deconv2x2_lrelu_bwd: dw and db must be given together");
+    return deconv2x2_lrelu_bwd_fp32(Cin, Cout, H, W, slope, x, w, b, dy, dx, dw, db, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 size_t urnn_head_fwd_workspace_bytes(int32_t H, int32_t W) { return head_fwd_fp32_workspace(H, W); }

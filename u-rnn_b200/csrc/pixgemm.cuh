@@ -370,4 +370,169 @@ struct DeconvEpilogue {
     }
 };
 
+// out[row][pixel] = acc, rows routed by ranges to up to three destination maps (store / accumulate / skip): the
+// transposed-weight products of the backward pass (d input = W^T d output) land directly in dx / de / dh.
+struct RouteEpilogue {
+    static constexpr bool kAllowSmallTM = true;
+    float* dst[3]; int mend[3]; int mode[3];   // mode: 0 skip, 1 store, 2 accumulate
+    long plane;
+    template <int TM>
+    __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
+        if (p >= N) return;
+        const int nvalid = (N - p >= 4) ? 4 : (N - p);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int ch = m0 + pg_channel<TM>(ty, i);
+            if (ch >= M) continue;
+            int sg = (ch < mend[0]) ? 0 : ((ch < mend[1]) ? 1 : 2);
+            if (mode[sg] == 0) continue;
+            int c = ch - (sg == 0 ? 0 : mend[sg - 1]);
+            float* o = dst[sg] + (long)c * plane + p;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (u < nvalid) { if (mode[sg] == 1) o[u] = acc[i][u]; else o[u] += acc[i][u]; }
+        }
+    }
+};
+
+// Backward of the stems: pre = acc + bias is the recomputed pre-activation; out = dL/dpre = dy(gathered) * LeakyReLU'(pre).
+// kind 0: plain conv (dy[ch][p]); 1: conv + AvgPool2 (dy[ch][quad(p)] / 4); 2: 2x2 transposed conv, GEMM row
+// m = co*4 + dy*2 + dx of input pixel (y,x) reads dy_out[co][2y+dy][2x+dx].
+struct DpreEpilogue {
+    static constexpr bool kAllowSmallTM = true;
+    const float* bias; int bias_shift; const float* dy; float* out; long plane; int kind; int W; long dy_plane; float slope;
+    template <int TM>
+    __device__ __forceinline__ void run(float (&acc)[TM][4], int m0, int M, int ty, int tx, int p, int N) {
+        if (p >= N) return;
+        const int nvalid = (N - p >= 4) ? 4 : (N - p);
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int m = m0 + pg_channel<TM>(ty, i);
+            if (m >= M) continue;
+            float b = __ldg(bias + (m >> bias_shift));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u >= nvalid) break;
+                int q = p + u, y = q / W, x = q % W;
+                float g;
+                if (kind == 0)      g = __ldg(dy + (long)m * dy_plane + q);
+                else if (kind == 1) g = 0.25f * __ldg(dy + (long)m * dy_plane + (long)(y >> 1) * (W >> 1) + (x >> 1));
+                else                g = __ldg(dy + (long)(m >> 2) * dy_plane + (long)(2 * y + ((m >> 1) & 1)) * (2 * W) + 2 * x + (m & 1));
+                float pre = acc[i][u] + b;
+                out[(long)m * plane + q] = (pre > 0.f) ? g : g * slope;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ launch helpers
+template <class BL, class EP>
+static inline int launch_pixgemm(AView A, int M, int K, int N, const BL& bl, const EP& ep, bool need_gn, cudaStream_t st) {
+    int tm;
+    if (need_gn) {
+        if (M % 128 == 0) tm = 16; else if (M % 96 == 0) tm = 12; else if (M % 64 == 0) tm = 8; else tm = 4;
+        if (M % (8 * tm) != 0) { set_error("pixgemm: M=%d is not a multiple of 32", M); return URNN_E_INVALID; }
+    } else {
+        tm = (M <= 16) ? 2 : (M <= 32) ? 4 : (M <= 64) ? 8 : (M <= 96 || M % 96 == 0) ? 12 : 16;
+    }
+    dim3 grid((N + PG_BN - 1) / PG_BN, (M + 8 * tm - 1) / (8 * tm));
+    switch (tm) {
+        case 16: pixgemm_kernel<16, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
+        case 12: pixgemm_kernel<12, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
+        case 8:  pixgemm_kernel<8, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
+        case 4:  pixgemm_kernel<4, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
+        default:
+            if constexpr (EP::kAllowSmallTM) { pixgemm_kernel<2, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break; }
+            else { set_error("pixgemm: unsupported tile"); return URNN_E_INVALID; }
+    }
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ weight gradients
+// dW[m][k] += sum_p A[m][p] * B[k][p]   (A: a plain [M][N] map of output gradients, B: any pixel-GEMM loader)
+// db[m >> db_shift] += sum_p A[m][p].   Pixels are split over blockIdx.x; partial tiles are combined with atomics
+// (fp32 atomics: summation order is not fixed, like cuDNN's weight-gradient kernels).
+template <class BLoader>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const float* __restrict__ A, long a_plane, int M, int K, int N, BLoader bl, float* dW, long w_sm, long w_sk,
+             float* db, int db_shift, int pix_per_cta) {
+    __shared__ __align__(16) float As[32][64 + 4];
+    __shared__ __align__(16) float Bs[32][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, k0 = blockIdx.z * 64;
+    const int pbeg = blockIdx.x * pix_per_cta;
+    const int pend = (pbeg + pix_per_cta < N) ? (pbeg + pix_per_cta) : N;
+    float acc[4][4];
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+    bl.init(pbeg, N);
+    for (int ps = pbeg; ps < pend; ps += 32) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int idx = tid + i * 256;               // 512 float4 slots: 64 rows x 8 pixel quads
+            int row = idx >> 3, q = idx & 7, p = ps + q * 4;
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m0 + row < M) {
+                const float* src = A + (long)(m0 + row) * a_plane + p;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (p + u < pend) a4[u] = __ldg(src + u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) As[q * 4 + u][row] = a4[u];
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + row < K && p < pend) b4 = bl.load4(k0 + row, p, N);
+            const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Bs[q * 4 + u][row] = (p + u < pend) ? bv[u] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int px = 0; px < 32; ++px) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[px][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[px][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                rs[i] += av[i];
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + tx * 4 + j;
+            if (k < K) atomicAdd(dW + (long)m * w_sm + (long)k * w_sk, acc[i][j]);
+        }
+        if (db != nullptr && blockIdx.z == 0 && tx == 0) atomicAdd(db + (m >> db_shift), rs[i]);
+    }
+}
+
+template <class BL>
+static inline int launch_wgrad(const float* A, long a_plane, int M, int K, int N, const BL& bl, float* dW, long w_sm, long w_sk,
+                               float* db, int db_shift, cudaStream_t st) {
+    const int pix = 2048;
+    dim3 grid((N + pix - 1) / pix, (M + 63) / 64, (K + 63) / 64);
+    wgrad_kernel<BL><<<grid, 256, 0, st>>>(A, a_plane, M, K, N, bl, dW, w_sm, w_sk, db, db_shift, pix);
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
+
+// single-map loader helper
+static inline SegLoader single_map_loader(const float* x, int C, long plane) {
+    SegLoader L;
+    L.src[0] = L.src[1] = L.src[2] = x; L.cnt[0] = C; L.cnt[1] = L.cnt[2] = 0;
+    L.cend[0] = L.cend[1] = L.cend[2] = C; L.plane = plane;
+    L.gate_pre = nullptr; L.gate_scale = nullptr; L.gate_shift = nullptr; L.gate_ch0 = 0;
+    L.vec = (plane % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    return L;
+}
+
 }  // namespace urnn

@@ -6,30 +6,6 @@
 
 namespace urnn {
 
-// ------------------------------------------------------------------------------------------------ launch helpers
-template <class BL, class EP>
-static int launch_pixgemm(AView A, int M, int K, int N, const BL& bl, const EP& ep, bool need_gn, cudaStream_t st) {
-    int tm;
-    if (need_gn) {
-        if (M % 128 == 0) tm = 16; else if (M % 96 == 0) tm = 12; else if (M % 64 == 0) tm = 8; else tm = 4;
-        if (M % (8 * tm) != 0) { set_error("pixgemm: M=%d is not a multiple of 32", M); return URNN_E_INVALID; }
-    } else {
-        tm = (M <= 16) ? 2 : (M <= 32) ? 4 : (M <= 64) ? 8 : (M <= 96 || M % 96 == 0) ? 12 : 16;
-    }
-    dim3 grid((N + PG_BN - 1) / PG_BN, (M + 8 * tm - 1) / (8 * tm));
-    switch (tm) {
-        case 16: pixgemm_kernel<16, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
-        case 12: pixgemm_kernel<12, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
-        case 8:  pixgemm_kernel<8, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
-        case 4:  pixgemm_kernel<4, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break;
-        default:
-            if constexpr (EP::kAllowSmallTM) { pixgemm_kernel<2, BL, EP><<<grid, 256, 0, st>>>(A, M, K, N, bl, ep); break; }
-            else { set_error("pixgemm: unsupported tile"); return URNN_E_INVALID; }
-    }
-    URNN_LAUNCH_CHECK();
-    return URNN_OK;
-}
-
 // ------------------------------------------------------------------------------------------------ cell, fp32
 // h_out = (1-z)*h + z*tanh(GN2(C)),  z = sigmoid(GN1(G)[:F])           (ConvRNN.py:160-162,180,185,189)
 __global__ void __launch_bounds__(256)
@@ -111,8 +87,9 @@ static void fill_segments(Loader& L, const urnn_cell_desc* d, const float* x, co
     L.vec = (L.plane % 4 == 0) && aligned16(x) && aligned16(e) && aligned16(h);
 }
 
-int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
-                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+// sweeps A and B only (pre-GN maps G, C and the folded GroupNorm affines stay in the workspace view `w`)
+int cgru_fwd_fp32_passes(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+                         const float* h, CellWsView* wout, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int F = d->F, ks = d->ksize, kk = ks * ks;
     const long N = (long)d->H * d->W;
     const int Ch = (d->variant == URNN_CELL_DECODER) ? 2 * F : F;
@@ -149,7 +126,15 @@ int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
         L.gate_pre = w.G; L.gate_scale = w.scale1; L.gate_shift = w.shift1; L.gate_ch0 = F;
         URNN_TRY(launch_pixgemm(A2, F, Keff * kk, (int)N, L, ep2, true, st));
     }
-    return cgru_blend_launch(w, h, h_out, F, N, st);
+    *wout = w;
+    return URNN_OK;
+}
+
+int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    CellWsView w;
+    URNN_TRY(cgru_fwd_fp32_passes(d, p, x, e, h, &w, ws, ws_bytes, st));
+    return cgru_blend_launch(w, h, h_out, d->F, (long)d->H * d->W, st);
 }
 
 // ------------------------------------------------------------------------------------------------ stems

@@ -31,6 +31,8 @@ int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const v
                            const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
 
 // fp32 FFMA path (urnn_fp32.cu)
+int cgru_fwd_fp32_passes(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
+                         const float* h, CellWsView* wout, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t cgru_fwd_fp32_workspace(const urnn_cell_desc* d);
 int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -41,5 +43,18 @@ int deconv2x2_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, float slope, const
 size_t head_fwd_fp32_workspace(int H, int W);
 int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
                   const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// backward, fp32 (urnn_bwd.cu)
+size_t conv1x1_lrelu_bwd_workspace(int Cin, int Cout, int H, int W, int pool);
+int conv1x1_lrelu_bwd_fp32(int Cin, int Cout, int H, int W, int pool, float slope, const float* x, const float* w,
+                           const float* b, const float* dy, float* dx, float* dw, float* db, void* ws, size_t ws_bytes,
+                           cudaStream_t st);
+size_t deconv2x2_lrelu_bwd_workspace(int Cin, int Cout, int H, int W);
+int deconv2x2_lrelu_bwd_fp32(int Cin, int Cout, int H, int W, float slope, const float* x, const float* w, const float* b,
+                             const float* dy, float* dx, float* dw, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t cgru_bwd_workspace(const urnn_cell_desc* d);
+int cgru_bwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e, const float* h,
+                  const float* dh_out, float* dx, float* de, float* dh, const urnn_cell_grads* gr, void* ws, size_t ws_bytes,
+                  cudaStream_t st);
 
 }  // namespace urnn
