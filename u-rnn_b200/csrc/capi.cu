@@ -140,10 +140,12 @@ int urnn_head_fwd(int32_t H, int32_t W, float cls_thred, float ln_eps, float slo
     URNN_CHECK_ARG(H > 0 && W > 0 && p && feat && out, "head: bad argument");
     return head_fwd_fp32(H, W, cls_thred, ln_eps, slope, p, feat, out, ws, ws_bytes, (cudaStream_t)stream);
 }
-size_t urnn_head_bwd_workspace_bytes(int32_t, int32_t) { return 0; }
-int urnn_head_bwd(int32_t, int32_t, float, float, float, const urnn_head_params*, const float*, const float*,
-                  float*, const urnn_head_grads*, void*, size_t, void*) {
-    set_error("head_bwd: not implemented in this build"); return URNN_E_UNSUPPORTED;
+size_t urnn_head_bwd_workspace_bytes(int32_t H, int32_t W) { return head_bwd_workspace(H, W); }
+int urnn_head_bwd(int32_t H, int32_t W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
+                  const float* feat, const float* dout, float* dfeat, const urnn_head_grads* grads, void* ws,
+                  size_t ws_bytes, void* stream) {
+    URNN_CHECK_ARG(H > 0 && W > 0 && p && feat && dout && dfeat && grads && ws, "head_bwd: bad argument");
+    return head_bwd_fp32(H, W, cls_thred, ln_eps, slope, p, feat, dout, dfeat, grads, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------ whole step

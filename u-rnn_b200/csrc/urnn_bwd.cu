@@ -8,6 +8,7 @@
 //   dx = rstd * (gamma*dy - mean_g(gamma*dy) - xhat * mean_g(gamma*dy*xhat)).
 // Gradients of a bf16-mode forward are computed by this fp32 path as well (recompute in fp32).
 #include "pixgemm.cuh"
+#include "head_bwd.cuh"
 #include "urnn_internal.h"
 
 namespace urnn {
@@ -276,6 +277,59 @@ int cgru_bwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
         for (int i = 0; i < 3; ++i) { int j = i < n ? i : n - 1; re.mend[i] = ends[j]; re.dst[i] = dsts[j]; re.mode[i] = modes[j]; }
         URNN_TRY(launch_pixgemm(AView{p->w1 + aoff, 1, (long)Ktot}, Keff, 2 * F, (int)N, Ld, re, false, st));
     }
+    return URNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ head
+struct HeadBwdWs { float2* partial; double2* total; unsigned* counter; double *bsum, *psum; float* m[4]; int gx; };
+static size_t head_bwd_layout(int H, int W, void* ws, size_t ws_bytes, HeadBwdWs* out) {
+    const long N = (long)H * W;
+    Arena a(ws, ws_bytes);
+    HeadBwdWs w;
+    w.gx = (int)((N + 127) / 128);
+    w.counter = a.take<unsigned>(64);
+    w.total = a.take<double2>(8);
+    w.bsum = a.take<double>(16);
+    w.psum = a.take<double>(40);
+    w.partial = a.take<float2>((size_t)5 * w.gx);
+    for (int i = 0; i < 4; ++i) w.m[i] = a.take<float>((size_t)16 * N);
+    if (out) *out = w;
+    return align_up(a.off, 256);
+}
+size_t head_bwd_workspace(int H, int W) { return head_bwd_layout(H, W, nullptr, 0, nullptr); }
+
+int head_bwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p, const float* feat,
+                  const float* dout, float* dfeat, const urnn_head_grads* g, void* ws, size_t ws_bytes, cudaStream_t st) {
+    CommDev comm; current_comm(&comm);
+    if (comm.world > 1) { set_error("head_bwd: spatially sharded backward is not implemented"); return URNN_E_UNSUPPORTED; }
+    HeadBwdWs w;
+    size_t need = head_bwd_layout(H, W, ws, ws_bytes, &w);
+    if (need > ws_bytes) { set_error("head_bwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
+    const long N = (long)H * W;
+    URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
+    URNN_CUDA(cudaMemsetAsync(w.bsum, 0, 16 * sizeof(double), st));
+    URNN_CUDA(cudaMemsetAsync(w.psum, 0, 40 * sizeof(double), st));
+    HeadBwdDev hb;
+    hb.fwd.p = *p; hb.fwd.cls_thred = cls_thred; hb.fwd.eps = ln_eps; hb.fwd.slope = slope; hb.fwd.plane = N;
+    hb.fwd.count = 16.0 * (double)N;
+    hb.fwd.sink = StatSink{w.partial, w.total, w.counter, 5, w.gx, comm};
+    hb.g = *g; hb.bsum = w.bsum; hb.psum = w.psum; hb.dout = dout; hb.dfeat = dfeat;
+    hb.m0 = w.m[0]; hb.m1 = w.m[1]; hb.m2 = w.m[2]; hb.m3 = w.m[3];
+    // forward statistics (three LayerNorm levels)
+    head_kernel<0><<<w.gx, 128, 0, st>>>(hb.fwd, feat, nullptr, (int)N); URNN_LAUNCH_CHECK();
+    head_kernel<1><<<w.gx, 128, 0, st>>>(hb.fwd, feat, nullptr, (int)N); URNN_LAUNCH_CHECK();
+    head_kernel<2><<<w.gx, 128, 0, st>>>(hb.fwd, feat, nullptr, (int)N); URNN_LAUNCH_CHECK();
+    // backward sweeps
+    head_bwd_kernel<1><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();
+    head_pred_grads_kernel<<<1, 32, 0, st>>>(w.psum, *g); URNN_LAUNCH_CHECK();
+    head_bwd_kernel<2><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();
+    URNN_TRY(launch_wgrad(w.m[0], N, 16, 16, (int)N, single_map_loader(w.m[1], 16, N), g->conv_w[2], 16, 1, nullptr, 0, st));   // cls_convs.1
+    URNN_TRY(launch_wgrad(w.m[2], N, 16, 16, (int)N, single_map_loader(w.m[3], 16, N), g->conv_w[4], 16, 1, nullptr, 0, st));   // reg_convs.1
+    head_bwd_kernel<3><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();
+    URNN_TRY(launch_wgrad(w.m[0], N, 16, 16, (int)N, single_map_loader(w.m[1], 16, N), g->conv_w[1], 16, 1, nullptr, 0, st));   // cls_convs.0
+    URNN_TRY(launch_wgrad(w.m[2], N, 16, 16, (int)N, single_map_loader(w.m[1], 16, N), g->conv_w[3], 16, 1, nullptr, 0, st));   // reg_convs.0
+    head_bwd_kernel<4><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();
+    URNN_TRY(launch_wgrad(w.m[0], N, 16, 16, (int)N, single_map_loader(feat, 16, N), g->conv_w[0], 16, 1, nullptr, 0, st));     // stems
     return URNN_OK;
 }
 

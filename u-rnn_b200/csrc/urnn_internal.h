@@ -52,6 +52,9 @@ int conv1x1_lrelu_bwd_fp32(int Cin, int Cout, int H, int W, int pool, float slop
 size_t deconv2x2_lrelu_bwd_workspace(int Cin, int Cout, int H, int W);
 int deconv2x2_lrelu_bwd_fp32(int Cin, int Cout, int H, int W, float slope, const float* x, const float* w, const float* b,
                              const float* dy, float* dx, float* dw, float* db, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t head_bwd_workspace(int H, int W);
+int head_bwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p, const float* feat,
+                  const float* dout, float* dfeat, const urnn_head_grads* g, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t cgru_bwd_workspace(const urnn_cell_desc* d);
 int cgru_bwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e, const float* h,
                   const float* dh_out, float* dx, float* de, float* dh, const urnn_cell_grads* gr, void* ws, size_t ws_bytes,
