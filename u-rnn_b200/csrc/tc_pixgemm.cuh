@@ -354,16 +354,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 }
             }
         };
-        auto issue = [&](int tile, int kb, Buf& b) {
+        const ChanEnt* myent = ctab + ch0;
+        const long px_off = (long)px8 * 8;
+        // fast path: the whole tile is inside the map and every plane is vector-aligned -> no per-element control flow
+        auto issue_fast = [&](int tile, int kb, Buf& b) {
+            const long eoff = (long)tile * TILE_M + px_off;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const ChanEnt e = myent[kb * KBLK + 32 * c];
+                b.meta[c] = e.meta;
+                if (e.meta & 1) {
+                    if (e.meta & 2) {
+                        const uint2* s = reinterpret_cast<const uint2*>(e.ptr + eoff * 2);
+                        const uint2 w0 = __ldg(s), w1 = __ldg(s + 1);
+                        unpack_bf16x2(w0.x, b.v[c][0], b.v[c][1]); unpack_bf16x2(w0.y, b.v[c][2], b.v[c][3]);
+                        unpack_bf16x2(w1.x, b.v[c][4], b.v[c][5]); unpack_bf16x2(w1.y, b.v[c][6], b.v[c][7]);
+                    } else {
+                        const float4* s = reinterpret_cast<const float4*>(e.ptr + eoff * 4);
+                        const float4 lo = __ldg(s), hi = __ldg(s + 1);
+                        b.v[c][0] = lo.x; b.v[c][1] = lo.y; b.v[c][2] = lo.z; b.v[c][3] = lo.w;
+                        b.v[c][4] = hi.x; b.v[c][5] = hi.y; b.v[c][6] = hi.z; b.v[c][7] = hi.w;
+                    }
+                    if constexpr (GATED) {
+                        if (e.meta & 4) {
+                            const uint2* s = reinterpret_cast<const uint2*>(e.gptr + eoff * 2);
+                            const uint2 w0 = __ldg(s), w1 = __ldg(s + 1);
+                            unpack_bf16x2(w0.x, b.g[c][0], b.g[c][1]); unpack_bf16x2(w0.y, b.g[c][2], b.g[c][3]);
+                            unpack_bf16x2(w1.x, b.g[c][4], b.g[c][5]); unpack_bf16x2(w1.y, b.g[c][6], b.g[c][7]);
+                            b.sc[c] = e.sc; b.sh[c] = e.sh;
+                        }
+                    }
+                }
+            }
+        };
+        auto issue_slow = [&](int tile, int kb, Buf& b) {
             const long p = (long)tile * TILE_M + px8 * 8;
             const int nvalid = (p >= N) ? 0 : ((N - p >= 8) ? 8 : (int)(N - p));
             const bool whole = aligned && nvalid == 8;
 #pragma unroll
-            const int kvalid = (kb == nkb - 1) ? last_k : KBLK;
-#pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const ChanEnt e = ctab[kb * KBLK + ch0 + 32 * c];
-                b.meta[c] = (nvalid > 0 && ch0 + 32 * c < kvalid) ? e.meta : 0;
+                const ChanEnt e = myent[kb * KBLK + 32 * c];
+                b.meta[c] = (nvalid > 0) ? e.meta : 0;
                 if (b.meta[c] & 1) {
                     if constexpr (EPI == EPI_POOL) {
                         load8_quads(reinterpret_cast<const float*>(e.ptr), p >> 2, (long)N >> 2, P.img_w >> 1, P.img_w, b.v[c]);
@@ -376,12 +407,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 }
             }
         };
+        auto issue = [&](int tile, int kb, Buf& b) {
+            if (EPI != EPI_POOL && aligned && (long)(tile + 1) * TILE_M <= N) issue_fast(tile, kb, b);
+            else issue_slow(tile, kb, b);
+        };
         auto commit = [&](int kb, int stage, Buf& b) {
             uint8_t* st = sm + a_off + stage * STAGE_BYTES;
-            const int kvalid = (kb == nkb - 1) ? last_k : KBLK;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                if (ch0 + 32 * c < kvalid) {
+                {   // channels past K were tabulated as invalid: they are stored as zeros (or never read by the MMA)
                     uint4 pk = make_uint4(0u, 0u, 0u, 0u);
                     if (b.meta[c] & 1) {
                         if constexpr (GATED) {
