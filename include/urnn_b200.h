@@ -193,6 +193,25 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
                           const float* inputs_host, float* out_host, float* const* states,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* The same loop for one rainfall EVENT given as the dataset provides it (dataset/Dynamic2DFlood.py:200-236): three
+ * static maps and a scalar rainfall series, all on the HOST.  Replaces test.py:356-375 INCLUDING the per-step input
+ * assembly preprocess_inputs (dataset/Dynamic2DFlood.py:265-366): the dense (C_in,H,W) tensor is never built.  With
+ * scalar rainfall 2*hist of the C_in channels are spatially constant, so their contribution to the stage-1 stem
+ * (1x1 conv) is folded into a per-step bias, b_t = b + W[:, :2h] . [rain(t-h+1..t)/rain_max | cumsum(..)/cumsum_max]
+ * (zero-padded before the event start), and the stem reads only the 3 normalised static maps
+ * (DEM-min)/(max-min), (impervious-0.05)/0.9, manhole.  H2D traffic: 3 maps + 2T scalars per event.
+ * d->Cin must equal 2*hist + 3.  states[6] are updated in place; out_host (T,H,W) receives the masked depth. */
+typedef struct urnn_event_desc {
+    int32_t T, hist;                  /* time steps of the event, historical_nums */
+    float rain_max, cumsum_rain_max;  /* MinMaxScaler bounds of the rainfall channels */
+    float dem_min, dem_max;           /* per-event DEM bounds (inputs["min_DEM"], inputs["max_DEM"]) */
+} urnn_event_desc;
+size_t urnn_ed_event_host_workspace_bytes(const urnn_ed_desc* d, const urnn_event_desc* ev);
+int urnn_ed_event_host(const urnn_ed_desc* d, const urnn_ed_params* p, const urnn_event_desc* ev,
+                       const float* dem_host, const float* impervious_host, const float* manhole_host,
+                       const float* rainfall_host, const float* cumsum_rainfall_host,
+                       float* out_host, float* const* states, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Spatial sharding across the GPUs of one NVLink/NVSwitch box (one process per GPU).  The reference never shards
  * the grid (its only parallelism is DDP over events, main.py:385-387); this is the B200 scaling axis of the path.

@@ -265,3 +265,29 @@ def test_sequence_host_entry_point():
         assert torch.equal(out_host, depth.cpu())
         for a, b in zip(final_h, final):
             assert torch.equal(a, b)
+
+
+def test_event_entry_point_equals_dense_inputs():
+    """urnn_ed_event_host (raw maps + scalar rainfall series, rainfall folded into a per-step stage-1 bias) reproduces
+    the dense-input loop built with the reference's preprocess_inputs recipe (fp32: summation order only)."""
+    from urnn_b200.runner import SequenceRunner
+    H, W, hist, T = 24, 40, 3, 7
+    rng = np.random.RandomState(42)                  # same draws as O.synthetic_event_inputs
+    dem = rng.rand(H, W) * 10.0
+    imperv = rng.rand(H, W)
+    manhole = (rng.rand(H, W) > 0.95).astype(np.float64)
+    rain = rng.rand(T) * 30.0
+    xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, hist)).to(DEV)
+    net = build_ed(H, W, 2 * hist + 3)
+    runner = SequenceRunner(net, H, W, 2 * hist + 3, use_graph=False)
+    depth, _, final = runner.run(xs)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    rain32 = f32(rain)
+    out_host, final_e = runner.run_event_host(f32(dem), f32(imperv), f32(manhole), rain32, torch.cumsum(rain32, 0), hist, 60.0, 250.0)
+    ref = depth.cpu().numpy()
+    got = out_host.numpy()
+    same_mask = (ref != 0) == (got != 0)
+    assert same_mask.mean() > 0.999
+    np.testing.assert_allclose(got[same_mask], ref[same_mask], atol=2e-5, rtol=1e-4)
+    for a, b in zip(final_e, final):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-5, rtol=1e-4)

@@ -94,9 +94,9 @@ int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int3
     URNN_CHECK_ARG(x && w && b && y, "conv1x1: null pointer");
 #ifndef URNN_NO_TC
     if (math == URNN_MATH_BF16 && Cout <= 256)
-        return conv1x1_lrelu_fwd_tc(Cin, Cout, H, W, pool, slope, x, 0, w, b, nullptr, y, (cudaStream_t)stream);
+        return conv1x1_lrelu_fwd_tc(Cin, Cout, H, W, pool, slope, x, 0, w, Cin, b, nullptr, y, (cudaStream_t)stream);
 #endif
-    return conv1x1_lrelu_fwd_fp32(Cin, Cout, H, W, pool, slope, x, w, b, y, (cudaStream_t)stream);
+    return conv1x1_lrelu_fwd_fp32(Cin, Cout, H, W, pool, slope, x, w, Cin, b, y, (cudaStream_t)stream);
 }
 size_t urnn_conv1x1_lrelu_bwd_workspace_bytes(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int32_t pool) {
     return conv1x1_lrelu_bwd_workspace(Cin, Cout, H, W, pool);
@@ -199,11 +199,17 @@ size_t urnn_ed_step_workspace_bytes(const urnn_ed_desc* d) {
     return pl.total;
 }
 
-int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float* input,
-                     const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes,
-                     void* stream) {
+// The stage-1 stem as the step sees it.  Dense input: {input, Cin, W, Cin, b}.  Event mode (scalar rainfall): the 2*hist
+// rainfall channels are spatially constant, so their contribution W[:, :2h].r_t is folded into a per-step bias and the
+// stem only reads the 3 static maps: {static3, 3, W + 2h, Cin, b_t}.
+struct Stem1 { const float* x; int cin; const float* w; long w_ld; const float* b; };
+
+static int ed_step_impl(const urnn_ed_desc* d, const urnn_ed_params* p, const Stem1& s1,
+                        const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes,
+                        void* stream) {
     EdPlan pl;
     URNN_TRY(ed_plan(d, ws, ws_bytes, &pl));
+    const float* input = s1.x;
     URNN_CHECK_ARG(p && input && sin && sout && out, "ed_step: null pointer");
     if (pl.total > ws_bytes) { set_error("ed_step: workspace %zu < %zu bytes", ws_bytes, pl.total); return URNN_E_WORKSPACE; }
     for (int i = 0; i < 6; ++i) URNN_CHECK_ARG(sin[i] && sout[i] && sin[i] != sout[i], "ed_step: state %d null or aliased", i);
@@ -214,11 +220,12 @@ int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float
         // tcgen05 route: stem outputs that only feed GEMMs are kept as bf16 maps (the consumer would round them anyway)
         __nv_bfloat16* sb[3] = {(__nv_bfloat16*)pl.s[0], (__nv_bfloat16*)pl.s[1], (__nv_bfloat16*)pl.s[2]};
         __nv_bfloat16 *up3 = (__nv_bfloat16*)pl.up3, *up2 = (__nv_bfloat16*)pl.up2;
-        const float* cur = input; int cin = d->Cin;
+        const float* cur = input; int cin = s1.cin;
         for (int k = 0; k < 3; ++k) {
             int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
-            URNN_TRY(conv1x1_lrelu_fwd_tc(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, 0, p->enc_stem_w[k],
-                                          p->enc_stem_b[k], sb[k], nullptr, st));
+            URNN_TRY(conv1x1_lrelu_fwd_tc(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, 0,
+                                          k == 0 ? s1.w : p->enc_stem_w[k], k == 0 ? s1.w_ld : (long)cin,
+                                          k == 0 ? s1.b : p->enc_stem_b[k], sb[k], nullptr, st));
             URNN_TRY(check_cell(&pl.enc[k], &p->enc_cell[k], nullptr, sin[k], sout[k]));
             URNN_TRY(cgru_fwd_bf16(&pl.enc[k], &p->enc_cell[k], sb[k], 1, nullptr, sin[k], sout[k], pl.cell_ws, pl.cell_ws_bytes, st));
             cur = sout[k]; cin = d->enc_gru[k];
@@ -230,17 +237,18 @@ int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float
         URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, sout[4], 0, p->dec_stem_w[1],
                                         p->dec_stem_b[1], up2, nullptr, st));
         URNN_TRY(cgru_fwd_bf16(&pl.dec[2], &p->dec_cell[2], up2, 1, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, st));
-        URNN_TRY(conv1x1_lrelu_fwd_tc(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], 0, p->dec_stem_w[2], p->dec_stem_b[2],
-                                      nullptr, pl.feat, st));
+        URNN_TRY(conv1x1_lrelu_fwd_tc(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], 0, p->dec_stem_w[2], d->dec_gru[2],
+                                      p->dec_stem_b[2], nullptr, pl.feat, st));
         return urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream);
     }
 #endif
     // ---- encoder (encoder.py:187-215): stem conv (+pool) then ConvGRU, stage k feeds stage k+1
-    const float* cur = input; int cin = d->Cin;
+    const float* cur = input; int cin = s1.cin;
     for (int k = 0; k < 3; ++k) {
         int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
-        URNN_TRY(urnn_conv1x1_lrelu_fwd(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, d->math, cur, p->enc_stem_w[k],
-                                        p->enc_stem_b[k], pl.s[k], stream));
+        URNN_TRY(conv1x1_lrelu_fwd_fp32(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur,
+                                        k == 0 ? s1.w : p->enc_stem_w[k], k == 0 ? s1.w_ld : (long)cin,
+                                        k == 0 ? s1.b : p->enc_stem_b[k], pl.s[k], st));
         URNN_TRY(urnn_cgru_fwd(&pl.enc[k], &p->enc_cell[k], pl.s[k], nullptr, sin[k], sout[k], pl.cell_ws,
                                pl.cell_ws_bytes, stream));
         cur = sout[k]; cin = d->enc_gru[k];
@@ -283,6 +291,14 @@ static int seq_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, SeqPlan* s
     sp->step_ws = a.take<char>(pl.total);
     sp->total = align_up(a.off, 256);
     return URNN_OK;
+}
+
+int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float* input,
+                     const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes,
+                     void* stream) {
+    URNN_CHECK_ARG(d && p, "ed_step: null descriptor/params");
+    Stem1 s1{input, d->Cin, p->enc_stem_w[0], (long)d->Cin, p->enc_stem_b[0]};
+    return ed_step_impl(d, p, s1, sin, sout, out, ws, ws_bytes, stream);
 }
 
 size_t urnn_ed_sequence_host_workspace_bytes(const urnn_ed_desc* d) {
@@ -340,6 +356,120 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
     if (T & 1) {                                            // final states live in the workspace buffers: copy back
         for (int k = 0; k < 6; ++k)
             URNN_CUDA(cudaMemcpyAsync(sp.st[0][k], sp.st[1][k], sp.state_elems[k] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    URNN_CUDA(cudaStreamSynchronize(s_out));
+    URNN_CUDA(cudaStreamSynchronize(st));
+    return URNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ event mode
+__global__ void event_static_maps_kernel(const float* __restrict__ dem, const float* __restrict__ imp,
+                                         const float* __restrict__ man, float dem_min, float dem_max,
+                                         float* __restrict__ out, long N) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    out[i] = (dem[i] - dem_min) / (dem_max - dem_min);          // MinMaxScaler, Dynamic2DFlood.py:289-292,369-377
+    out[N + i] = (imp[i] - 0.05f) / (0.95f - 0.05f);
+    out[2 * N + i] = (man[i] - 0.f) / (1.f - 0.f);
+}
+
+// bias_all[t][o] = b[o] + sum_j W[o][j] rain_n(t-h+1+j) + sum_j W[o][h+j] cum_n(t-h+1+j)   (zero before the event start)
+__global__ void event_fold_rain_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ rain,
+                                       const float* __restrict__ cum, int T, int hist, int cin, int cout, float rain_max,
+                                       float cum_max, float* __restrict__ bias_all) {
+    int t = blockIdx.x, o = threadIdx.x;
+    if (o >= cout) return;
+    float acc = b[o];
+    for (int j = 0; j < hist; ++j) {
+        int s = t - hist + 1 + j;
+        if (s < 0) continue;
+        acc = fmaf(w[(long)o * cin + j], (rain[s] - 0.f) / (rain_max - 0.f), acc);
+        acc = fmaf(w[(long)o * cin + hist + j], (cum[s] - 0.f) / (cum_max - 0.f), acc);
+    }
+    bias_all[(long)t * cout + o] = acc;
+}
+
+struct EventPlan { float* raw; float* maps; float* series; float* bias_all; float* out[2]; float* st[6]; size_t state_elems[6];
+                   void* step_ws; size_t step_ws_bytes; size_t total; };
+static int event_plan(const urnn_ed_desc* d, const urnn_event_desc* ev, void* ws, size_t ws_bytes, EventPlan* ep) {
+    URNN_CHECK_ARG(d && ev && ev->T > 0 && ev->hist >= 0, "ed_event: bad descriptor");
+    URNN_CHECK_ARG(d->Cin == 2 * ev->hist + 3, "ed_event: Cin=%d must equal 2*hist+3 (hist=%d)", d->Cin, ev->hist);
+    EdPlan pl;
+    URNN_TRY(ed_plan(d, nullptr, 0, &pl));
+    const size_t N = (size_t)d->H * d->W;
+    const int ch[6] = {d->enc_gru[0], d->enc_gru[1], d->enc_gru[2], d->dec_gru[0], d->dec_gru[1], d->dec_gru[2]};
+    const int sc[6] = {0, 1, 2, 2, 1, 0};
+    Arena a(ws, ws_bytes);
+    ep->raw = a.take<float>(3 * N);
+    ep->maps = a.take<float>(3 * N);
+    ep->series = a.take<float>(2 * (size_t)ev->T);
+    ep->bias_all = a.take<float>((size_t)ev->T * d->enc_conv[0]);
+    for (int i = 0; i < 2; ++i) ep->out[i] = a.take<float>(2 * N);
+    for (int k = 0; k < 6; ++k) { ep->state_elems[k] = (size_t)ch[k] * (N >> (2 * sc[k])); ep->st[k] = a.take<float>(ep->state_elems[k]); }
+    ep->step_ws_bytes = pl.total;
+    ep->step_ws = a.take<char>(pl.total);
+    ep->total = align_up(a.off, 256);
+    return URNN_OK;
+}
+
+size_t urnn_ed_event_host_workspace_bytes(const urnn_ed_desc* d, const urnn_event_desc* ev) {
+    EventPlan ep;
+    if (event_plan(d, ev, nullptr, 0, &ep) != URNN_OK) return 0;
+    return ep.total;
+}
+
+int urnn_ed_event_host(const urnn_ed_desc* d, const urnn_ed_params* p, const urnn_event_desc* ev, const float* dem_host,
+                       const float* impervious_host, const float* manhole_host, const float* rainfall_host,
+                       const float* cumsum_rainfall_host, float* out_host, float* const* states, void* ws,
+                       size_t ws_bytes, void* stream) {
+    URNN_CHECK_ARG(p && dem_host && impervious_host && manhole_host && rainfall_host && cumsum_rainfall_host && out_host && states,
+                   "ed_event: null pointer");
+    EventPlan ep;
+    URNN_TRY(event_plan(d, ev, ws, ws_bytes, &ep));
+    if (ep.total > ws_bytes) { set_error("ed_event: workspace %zu < %zu bytes", ws_bytes, ep.total); return URNN_E_WORKSPACE; }
+    static cudaStream_t s_out = nullptr;
+    static cudaEvent_t ev_step[2], ev_out[2], ev_start;
+    if (s_out == nullptr) {
+        URNN_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        URNN_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            URNN_CUDA(cudaEventCreateWithFlags(&ev_step[i], cudaEventDisableTiming));
+            URNN_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)d->H * d->W;
+    const int T = ev->T, cout0 = d->enc_conv[0];
+    // ---- once per event: upload (3 maps + 2T scalars), normalise, fold the rainfall into T stage-1 biases
+    URNN_CUDA(cudaMemcpyAsync(ep.raw, dem_host, N * sizeof(float), cudaMemcpyHostToDevice, st));
+    URNN_CUDA(cudaMemcpyAsync(ep.raw + N, impervious_host, N * sizeof(float), cudaMemcpyHostToDevice, st));
+    URNN_CUDA(cudaMemcpyAsync(ep.raw + 2 * N, manhole_host, N * sizeof(float), cudaMemcpyHostToDevice, st));
+    URNN_CUDA(cudaMemcpyAsync(ep.series, rainfall_host, T * sizeof(float), cudaMemcpyHostToDevice, st));
+    URNN_CUDA(cudaMemcpyAsync(ep.series + T, cumsum_rainfall_host, T * sizeof(float), cudaMemcpyHostToDevice, st));
+    event_static_maps_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ep.raw, ep.raw + N, ep.raw + 2 * N, ev->dem_min, ev->dem_max, ep.maps, (long)N);
+    URNN_LAUNCH_CHECK();
+    URNN_CHECK_ARG(cout0 <= 1024, "ed_event: stage-1 width %d too large", cout0);
+    event_fold_rain_kernel<<<T, ((cout0 + 31) / 32) * 32, 0, st>>>(p->enc_stem_w[0], p->enc_stem_b[0], ep.series, ep.series + T, T, ev->hist,
+                                                                   d->Cin, cout0, ev->rain_max, ev->cumsum_rain_max, ep.bias_all);
+    URNN_LAUNCH_CHECK();
+    URNN_CUDA(cudaEventRecord(ev_start, st));
+    URNN_CUDA(cudaStreamWaitEvent(s_out, ev_start, 0));
+    // ---- T steps, states ping-pong between the caller's buffers and the workspace
+    for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        if (t >= 2) URNN_CUDA(cudaStreamWaitEvent(st, ev_out[b], 0));
+        const float* sin[6]; float* sout[6];
+        for (int k = 0; k < 6; ++k) { sin[k] = b ? ep.st[k] : states[k]; sout[k] = b ? states[k] : ep.st[k]; }
+        Stem1 s1{ep.maps, 3, p->enc_stem_w[0] + 2 * ev->hist, (long)d->Cin, ep.bias_all + (size_t)t * cout0};
+        URNN_TRY(ed_step_impl(d, p, s1, sin, sout, ep.out[b], ep.step_ws, ep.step_ws_bytes, stream));
+        URNN_CUDA(cudaEventRecord(ev_step[b], st));
+        URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
+        URNN_CUDA(cudaMemcpyAsync(out_host + (size_t)t * N, ep.out[b], N * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        URNN_CUDA(cudaEventRecord(ev_out[b], s_out));
+    }
+    if (T & 1) {
+        for (int k = 0; k < 6; ++k)
+            URNN_CUDA(cudaMemcpyAsync(states[k], ep.st[k], ep.state_elems[k] * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     URNN_CUDA(cudaStreamSynchronize(s_out));
     URNN_CUDA(cudaStreamSynchronize(st));

@@ -77,13 +77,13 @@ void tc_params_defaults(tc::GemmParams& P) {
 // ------------------------------------------------------------------------------------------------ stems on tcgen05
 // y = [AvgPool2](LeakyReLU(conv1x1(x) + b)); x fp32 (kind 0) or bf16 (kind 1); exactly one of y_bf16 / y_f32 is set
 int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope, const void* x, int xkind,
-                         const float* w, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st) {
+                         const float* w, long w_ld, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st) {
     if (Cout > 256) { set_error("conv1x1(bf16): Cout=%d > 256", Cout); return URNN_E_UNSUPPORTED; }
     if (pool == 2 && xkind != 0) { set_error("conv1x1(bf16): pooled stem needs an fp32 source"); return URNN_E_UNSUPPORTED; }
     tc::GemmParams P; tc_params_defaults(P);
     P.seg.src[0] = P.seg.src[1] = P.seg.src[2] = x; P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = xkind;
     P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = Cin; P.seg.plane = (long)H * W;
-    P.W = w; P.w_ld = Cin; P.w_ks = 1; P.nrow1 = 1 << 30;
+    P.W = w; P.w_ld = w_ld; P.w_ks = 1; P.nrow1 = 1 << 30;
     P.bias = b; P.nbias = Cout; P.NOUT = (Cout + 31) & ~31; P.nout_store = Cout; P.K = Cin;
     P.out = y_bf16; P.out_f32 = y_f32; P.slope = slope;
     if (pool == 1) { P.N = H * W; P.out_plane = (long)H * W; return tc_launch(P, tc::EPI_LRELU, st); }

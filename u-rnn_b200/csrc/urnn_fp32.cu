@@ -139,8 +139,8 @@ int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
 
 // ------------------------------------------------------------------------------------------------ stems
 int conv1x1_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, int pool, float slope, const float* x,
-                           const float* w, const float* b, float* y, cudaStream_t st) {
-    AView A{w, (long)Cin, 1};
+                           const float* w, long w_ld, const float* b, float* y, cudaStream_t st) {
+    AView A{w, w_ld, 1};
     if (pool == 1) {
         SegLoader L;
         L.src[0] = L.src[1] = L.src[2] = x; L.cnt[0] = Cin; L.cnt[1] = L.cnt[2] = 0;

@@ -26,7 +26,7 @@ int cgru_blend_launch(const CellWsView& w, const float* h, float* h_out, int F, 
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope, const void* x, int xkind,
-                         const float* w, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
+                         const float* w, long w_ld, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
 int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const void* x, int xkind, const float* w,
                            const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
 
@@ -37,7 +37,7 @@ size_t cgru_fwd_fp32_workspace(const urnn_cell_desc* d);
 int cgru_fwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int conv1x1_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, int pool, float slope, const float* x,
-                           const float* w, const float* b, float* y, cudaStream_t st);
+                           const float* w, long w_ld, const float* b, float* y, cudaStream_t st);
 int deconv2x2_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, float slope, const float* x, const float* w,
                              const float* b, float* y, cudaStream_t st);
 size_t head_fwd_fp32_workspace(int H, int W);

@@ -46,6 +46,11 @@ class EdDesc(C.Structure):
                 ("cls_thred", C.c_float), ("gn_eps", C.c_float), ("ln_eps", C.c_float), ("lrelu_slope", C.c_float)]
 
 
+class EventDesc(C.Structure):
+    _fields_ = [("T", C.c_int32), ("hist", C.c_int32), ("rain_max", C.c_float), ("cumsum_rain_max", C.c_float),
+                ("dem_min", C.c_float), ("dem_max", C.c_float)]
+
+
 class EdParams(C.Structure):
     _fields_ = [("enc_stem_w", fp * 3), ("enc_stem_b", fp * 3),
                 ("enc_cell", CellParams * 3), ("dec_cell", CellParams * 3),
@@ -81,6 +86,9 @@ SIGNATURES = {
     "urnn_ed_sequence_host_workspace_bytes": (sz, [C.POINTER(EdDesc)]),
     "urnn_ed_sequence_host": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), i32, vp, vp, C.POINTER(fp),
                                         vp, sz, vp]),
+    "urnn_ed_event_host_workspace_bytes": (sz, [C.POINTER(EdDesc), C.POINTER(EventDesc)]),
+    "urnn_ed_event_host": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), C.POINTER(EventDesc), vp, vp, vp, vp, vp, vp,
+                                     C.POINTER(fp), vp, sz, vp]),
     "urnn_comm_local_init": (C.c_int, [i32, i32, vp]),
     "urnn_comm_connect": (C.c_int, [vp]),
     "urnn_comm_destroy": (C.c_int, []),

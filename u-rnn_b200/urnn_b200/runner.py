@@ -112,3 +112,41 @@ class SequenceRunner:
                                               C.c_void_p(out_host.data_ptr()), sp, C.c_void_p(self._host_ws.data_ptr()),
                                               self._host_ws.numel(), stream), "urnn_ed_sequence_host")
         return out_host, [s.clone() for s in st]
+
+    @torch.no_grad()
+    def run_event_host(self, dem, impervious, manhole, rainfall, cumsum_rainfall, hist, rain_max, cumsum_rain_max,
+                       dem_min=None, dem_max=None, out_host=None, states=None):
+        """One rainfall event as the reference's dataset provides it (raw (H,W) maps and scalar (T,) series on the HOST)
+        -> (T,H,W) masked depth on the host, through `urnn_ed_event_host`: no dense per-step input tensor is ever built
+        (the 2*hist rainfall channels are folded into a per-step stage-1 bias)."""
+        lib = _capi.load()
+        T = int(rainfall.shape[0])
+        host = lambda t: t.detach().to(torch.float32).contiguous().cpu()
+        dem, impervious, manhole, rainfall, cumsum_rainfall = [host(t) for t in (dem, impervious, manhole, rainfall, cumsum_rainfall)]
+        if tuple(dem.shape[-2:]) != (self.H, self.W):
+            raise ValueError(f"run_event_host: maps must be {self.H}x{self.W}")
+        if self.Cin != 2 * hist + 3:
+            raise ValueError(f"run_event_host: the model expects C_in={self.Cin}, historical_nums={hist} gives {2 * hist + 3}")
+        ev = _capi.EventDesc(T, hist, float(rain_max), float(cumsum_rain_max),
+                             float(dem.min() if dem_min is None else dem_min), float(dem.max() if dem_max is None else dem_max))
+        if out_host is None:
+            out_host = torch.empty((T, self.H, self.W), dtype=torch.float32).pin_memory()
+        st = self.states[0]
+        for i, dst in enumerate(st):
+            if states is None:
+                dst.zero_()
+            else:
+                dst.copy_(states[i].reshape(dst.shape))
+        need = lib.urnn_ed_event_host_workspace_bytes(C.byref(self.desc), C.byref(ev))
+        if need == 0:
+            raise RuntimeError("urnn_ed_event_host_workspace_bytes: " + lib.urnn_last_error().decode())
+        if getattr(self, "_event_ws", None) is None or self._event_ws.numel() < need:
+            self._event_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        params = self.net.ed_params()
+        sp = (C.c_void_p * 6)(*[s.data_ptr() for s in st])
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _capi.check(lib.urnn_ed_event_host(C.byref(self.desc), C.byref(params), C.byref(ev), vp(dem), vp(impervious), vp(manhole),
+                                           vp(rainfall), vp(cumsum_rainfall), vp(out_host), sp, vp(self._event_ws),
+                                           self._event_ws.numel(), stream), "urnn_ed_event_host")
+        return out_host, [s.clone() for s in st]
