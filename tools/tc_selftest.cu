@@ -107,7 +107,7 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     if (N >= 15000) {
         const unsigned* tr = hdbg + 148 * 16; unsigned t0 = tr[0];
         printf("trace (us since setup done): kernel entry %.1f kernel end %.1f\n", ((int)(tr[6 * 64] - t0)) * 1e-3, (tr[5 * 64] - t0) * 1e-3);
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 8; ++i)
             printf("  tile %2d: prod_done %7.1f  mma_issued %7.1f  epi_start %7.1f  epi_end %7.1f\n", i, (tr[64 + i] - t0) * 1e-3,
                    (tr[128 + i] - t0) * 1e-3, (tr[192 + i] - t0) * 1e-3, (tr[256 + i] - t0) * 1e-3);
         cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -133,5 +133,6 @@ int main() {
     rc |= run(96, 200, 15625, 8, 96);
     rc |= run(192, 192, 15625, 0, 96);
     rc |= run(128, 224, 250000, 96, 64);
+    rc |= run(64, 64, 250000, 0, 64, true);
     return rc;
 }
