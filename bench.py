@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--width", type=int, default=W_DEF)
     ap.add_argument("--hist", type=int, default=HIST_DEF)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--value-only", action="store_true", help="device-resident throughput only (large grids: skips the e2e / roofline legs)")
     return ap.parse_args()
 
 
@@ -196,7 +197,7 @@ def run_ours(a):
     net = build_net(H, W, C, a.math, dev)
     runner = SequenceRunner(net, H, W, C, math=a.math, use_graph=False)
     desc, params = runner.desc, net.ed_params()
-    ring = 8
+    ring = 2 if a.value_only else 8
     xs_host = torch.from_numpy(synthetic_inputs(H, W, hist, ring)).pin_memory()
     xs_dev = xs_host.to(dev)
     out = torch.empty((2, H, W), device=dev)
@@ -233,6 +234,19 @@ def run_ours(a):
         launches = lib.urnn_launch_count() - n0
     sec = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     value = world * N * a.steps / sec
+
+    if a.value_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                              "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": {"fp32": "f32", "bf16": "bf16"}[a.math], "data": "synthetic",
+                              "config": {"workload": f"{world * H}x{W}, C_in={C}, ED step forward, value only", "math": a.math},
+                              "gpu_launches": int(launches), "clocks": clk.summary()}))
+        if dist is not None:
+            from urnn_b200 import dist as ud
+            ud.shutdown_spatial_sharding()
+            dist.destroy_process_group()
+        return
 
     # (2) end to end through the C ABI with HOST buffers (urnn_ed_sequence_host): per step one H2D copy of the
     #     (C_in,H,W) input from pinned memory and one D2H copy of the (H,W) depth map, overlapped with compute

@@ -26,7 +26,7 @@ static int check_cell(const urnn_cell_desc* d, const urnn_cell_params* p, const 
     URNN_CHECK_ARG(d->Cx >= 0, "cgru: Cx=%d", d->Cx);
     URNN_CHECK_ARG(d->ksize >= 1 && d->ksize % 2 == 1 && d->ksize <= 7, "cgru: filter_size=%d must be odd and <= 7", d->ksize);
     URNN_CHECK_ARG(d->variant == URNN_CELL_ENCODER || d->variant == URNN_CELL_DECODER, "cgru: bad variant %d", d->variant);
-    URNN_CHECK_ARG((long)d->H * d->W * 2 * d->F < (1L << 31), "cgru: grid too large for 32-bit tile indexing");
+    URNN_CHECK_ARG((long)d->H * d->W < (1L << 30), "cgru: more than 2^30 cells per map are not supported (32-bit pixel indices)");
     URNN_CHECK_ARG(h && h_out, "cgru: null state pointer");
     URNN_CHECK_ARG(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0, "cgru: h and h_out must be 16-byte aligned");
     URNN_CHECK_ARG((d->variant == URNN_CELL_DECODER) == (e != nullptr), "cgru: e must be given exactly for the decoder variant");

@@ -4,7 +4,7 @@
 // One persistent CTA per SM, 25 warps, warp-specialised:
 //   warps 0-7   epilogue : tcgen05.ld the accumulator (TMEM lane = pixel, column = output channel); fused epilogue
 //                          (bias, optional addend map, GroupNorm statistics, bf16 NCHW store)
-//   warps 8-23  producers: build the A tile.  It is stored MN-major (pixel-contiguous) exactly like the NCHW source,
+//   warps 8-23  producers (two independent groups of 8 warps, alternating ring slots): build the A tile.  It is stored MN-major (pixel-contiguous) exactly like the NCHW source,
 //                          so a thread moves 8 consecutive pixels of one channel (two 16-byte global loads -> 8 bf16
 //                          -> one 16-byte shared store) and a half-warp covers the 512 contiguous bytes a channel
 //                          contributes to the tile.  The channel axis is a virtual concatenation of up to three maps;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
     if (tid == 0) {
-        for (int s = 0; s < P.nstage; ++s) { mbar_init(full0 + 8 * s, NPROD); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < P.nstage; ++s) { mbar_init(full0 + 8 * s, NPROD / 2); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NEPI); }
         fence_barrier_init();
     }
@@ -317,18 +317,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         // j = (pixel%64)/8 stored at chunk position j ^ (k&7).  Units (tile, K block) are streamed two deep.
         const int pt = tid - NEPI;
         const Segs& S = P.seg;
-        const int ch0 = pt >> 4, px8 = pt & 15;               // chunk c handles channel-in-block ch0 + 32c, pixels px8*8..+7
+        // Two independent producer groups of 256 threads; group g fills the units (tile, K block) with index u = g (mod 2).
+        // A thread holds NO loads in flight when it publishes its unit: fence.proxy.async compiles to MEMBAR.ALL.CTA,
+        // which waits for every outstanding load of the thread, so a per-thread software prefetch would be serialised
+        // by the fence.  Memory-level parallelism comes from the two groups (and the 8-deep ring) instead.
+        const int grp = pt >> 8, tl = pt & 255;
+        const int ch0 = tl >> 4, px8 = tl & 15;               // chunk c handles channel-in-block ch0 + 16c, pixels px8*8..+7
+        constexpr int NCH = 4;
         int trace_i = 0;
-        // the unit loop only reads its channel's entry of the shared source table and adds the tile offset (no
-        // segment decode, no 64-bit multiplies, no per-element branches)
         bool aligned = (N & 3) == 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
             aligned = aligned && ((reinterpret_cast<uintptr_t>(S.src[i]) & (S.kind[i] ? 7 : 15)) == 0);
         if (GATED) aligned = aligned && ((reinterpret_cast<uintptr_t>(S.gate_pre) & 7) == 0);
+        // chunk c lives 2 K-atoms (2048 B) after chunk c-1: channel ch0 + 16c
         const uint32_t soff0 = (uint32_t)((px8 >> 3) * 8192 + (ch0 >> 3) * 1024 + (ch0 & 7) * 128 + (((px8 & 7) ^ (ch0 & 7)) << 4));
-        const uint32_t soff1 = soff0 + 4 * 1024;             // chunk 1 = channel ch0 + 32: four K atoms further
-        struct Buf { float v[2][8]; float g[GATED ? 2 : 1][8]; float sc[2], sh[2]; int meta[2]; };
+        const ChanEnt* myent = ctab + ch0;
+        const long px_off = (long)px8 * 8;
+        struct Buf { float v[NCH][8]; uint2 g[GATED ? NCH : 1][2]; float sc[GATED ? NCH : 1], sh[GATED ? NCH : 1]; int meta[NCH]; };
 
         auto ld8 = [&](const char* ptr, bool bf16, long tile, bool whole, int nvalid, float (&v)[8]) {
             if (!bf16) {
@@ -354,14 +360,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 }
             }
         };
-        const ChanEnt* myent = ctab + ch0;
-        const long px_off = (long)px8 * 8;
         // fast path: the whole tile is inside the map and every plane is vector-aligned -> no per-element control flow
         auto issue_fast = [&](int tile, int kb, Buf& b) {
             const long eoff = (long)tile * TILE_M + px_off;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const ChanEnt e = myent[kb * KBLK + 32 * c];
+            for (int c = 0; c < NCH; ++c) {
+                const ChanEnt e = myent[kb * KBLK + 16 * c];
                 b.meta[c] = e.meta;
                 if (e.meta & 1) {
                     if (e.meta & 2) {
@@ -378,9 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                     if constexpr (GATED) {
                         if (e.meta & 4) {
                             const uint2* s = reinterpret_cast<const uint2*>(e.gptr + eoff * 2);
-                            const uint2 w0 = __ldg(s), w1 = __ldg(s + 1);
-                            unpack_bf16x2(w0.x, b.g[c][0], b.g[c][1]); unpack_bf16x2(w0.y, b.g[c][2], b.g[c][3]);
-                            unpack_bf16x2(w1.x, b.g[c][4], b.g[c][5]); unpack_bf16x2(w1.y, b.g[c][6], b.g[c][7]);
+                            b.g[c][0] = __ldg(s); b.g[c][1] = __ldg(s + 1);
                             b.sc[c] = e.sc; b.sh[c] = e.sh;
                         }
                     }
@@ -392,8 +394,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             const int nvalid = (p >= N) ? 0 : ((N - p >= 8) ? 8 : (int)(N - p));
             const bool whole = aligned && nvalid == 8;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                const ChanEnt e = myent[kb * KBLK + 32 * c];
+            for (int c = 0; c < NCH; ++c) {
+                const ChanEnt e = myent[kb * KBLK + 16 * c];
                 b.meta[c] = (nvalid > 0) ? e.meta : 0;
                 if (b.meta[c] & 1) {
                     if constexpr (EPI == EPI_POOL) {
@@ -402,64 +404,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                         ld8(e.ptr, (e.meta & 2) != 0, tile, whole, nvalid, b.v[c]);
                     }
                     if constexpr (GATED) {
-                        if (e.meta & 4) { ld8(e.gptr, true, tile, whole, nvalid, b.g[c]); b.sc[c] = e.sc; b.sh[c] = e.sh; }
+                        if (e.meta & 4) {
+                            float gv[8];
+                            ld8(e.gptr, true, tile, whole, nvalid, gv);
+                            b.g[c][0] = make_uint2(pack_bf16(gv[0], gv[1]), pack_bf16(gv[2], gv[3]));
+                            b.g[c][1] = make_uint2(pack_bf16(gv[4], gv[5]), pack_bf16(gv[6], gv[7]));
+                            b.sc[c] = e.sc; b.sh[c] = e.sh;
+                        }
                     }
                 }
             }
         };
-        auto issue = [&](int tile, int kb, Buf& b) {
-            if (EPI != EPI_POOL && aligned && (long)(tile + 1) * TILE_M <= N) issue_fast(tile, kb, b);
-            else issue_slow(tile, kb, b);
-        };
         auto commit = [&](int kb, int stage, Buf& b) {
             uint8_t* st = sm + a_off + stage * STAGE_BYTES;
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                {   // channels past K were tabulated as invalid: they are stored as zeros (or never read by the MMA)
-                    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                    if (b.meta[c] & 1) {
-                        if constexpr (GATED) {
-                            if (b.meta[c] & 4) {
+            for (int c = 0; c < NCH; ++c) {
+                uint4 pk = make_uint4(0u, 0u, 0u, 0u);      // channels past K were tabulated as invalid: stored as zeros
+                if (b.meta[c] & 1) {
+                    if constexpr (GATED) {
+                        if (b.meta[c] & 4) {
+                            float gv[8];
+                            unpack_bf16x2(b.g[c][0].x, gv[0], gv[1]); unpack_bf16x2(b.g[c][0].y, gv[2], gv[3]);
+                            unpack_bf16x2(b.g[c][1].x, gv[4], gv[5]); unpack_bf16x2(b.g[c][1].y, gv[6], gv[7]);
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) b.v[c][u] *= sigmoid_fast(fmaf(b.g[c][u], b.sc[c], b.sh[c]));
-                            }
+                            for (int u = 0; u < 8; ++u) b.v[c][u] *= sigmoid_fast(fmaf(gv[u], b.sc[c], b.sh[c]));
                         }
-                        pk = make_uint4(pack_bf16(b.v[c][0], b.v[c][1]), pack_bf16(b.v[c][2], b.v[c][3]),
-                                        pack_bf16(b.v[c][4], b.v[c][5]), pack_bf16(b.v[c][6], b.v[c][7]));
                     }
-                    *reinterpret_cast<uint4*>(st + (c ? soff1 : soff0)) = pk;
+                    pk = make_uint4(pack_bf16(b.v[c][0], b.v[c][1]), pack_bf16(b.v[c][2], b.v[c][3]),
+                                    pack_bf16(b.v[c][4], b.v[c][5]), pack_bf16(b.v[c][6], b.v[c][7]));
                 }
+                *reinterpret_cast<uint4*>(st + soff0 + c * 2048) = pk;
             }
             fence_proxy_async();                             // generic-proxy stores -> visible to tcgen05.mma
             mbar_arrive(full0 + 8 * stage);
             if (warp == NEPI / 32 && kb == nkb - 1) { TC_TRACE(1, trace_i); ++trace_i; }
         };
 
-        int stage = 0; uint32_t phase = 0;
-        int tile = blockIdx.x, kb = 0;
-        Buf b0, b1;
-        bool have = tile < ntiles;
-        if (have) issue(tile, kb, b0);
-        while (have) {
-            // ---- even unit lives in b0; prefetch the next into b1
-            int ntile = tile, nkbi = kb + 1;
-            if (nkbi == nkb) { nkbi = 0; ntile += gridDim.x; }
-            bool nhave = ntile < ntiles;
-            if (nhave) issue(ntile, nkbi, b1);
+        Buf b;
+        for (long u = grp;; u += 2) {
+            const long ti = u / nkb;
+            const int kb = (int)(u - ti * nkb);
+            const long tile = blockIdx.x + ti * gridDim.x;
+            if (tile >= ntiles) break;
+            const int stage = (int)(u % P.nstage);
+            const uint32_t phase = (uint32_t)((u / P.nstage) & 1);
+            if (EPI != EPI_POOL && aligned && (tile + 1) * TILE_M <= N) issue_fast((int)tile, kb, b);
+            else issue_slow((int)tile, kb, b);
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            commit(kb, stage, b0);
-            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
-            if (!nhave) break;
-            // ---- odd unit lives in b1; prefetch the next into b0
-            tile = ntile; kb = nkbi;
-            ntile = tile; nkbi = kb + 1;
-            if (nkbi == nkb) { nkbi = 0; ntile += gridDim.x; }
-            nhave = ntile < ntiles;
-            if (nhave) issue(ntile, nkbi, b0);
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            commit(kb, stage, b1);
-            if (++stage == P.nstage) { stage = 0; phase ^= 1; }
-            tile = ntile; kb = nkbi; have = nhave;
+            commit(kb, stage, b);
         }
     } else if (warp == MMA_WARP) {
         // =========================================================================== MMA issuer
