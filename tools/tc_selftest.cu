@@ -16,8 +16,11 @@ using namespace urnn;
 static float bf16r(float f) { return __bfloat162float(__float2bfloat16(f)); }
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
-int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
-    printf("== NOUT=%d K=%d N=%d segs=(%d,%d,%d)\n", NOUT, K, N, c0, c1, K - c0 - c1); fflush(stdout);
+// mode bits: 1 = allow bulk producers, 2 = walk tiles in reverse, 4 = first segment is a bf16 map with padded planes
+int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1) {
+    const long Np = ((long)N + 127) / 128 * 128;
+    const bool x0bf = (mode & 4) && c0 > 0;
+    printf("== NOUT=%d K=%d N=%d segs=(%d,%d,%d) gated=%d mode=%d\n", NOUT, K, N, c0, c1, K - c0 - c1, (int)gated, mode); fflush(stdout);
     std::vector<float> hx((size_t)K * N), hw((size_t)NOUT * K), hb(NOUT), hg(NOUT, 1.f), hz(NOUT, 0.f);
     srand(1);
     for (auto& v : hx) v = (rand() / (float)RAND_MAX) * 2 - 1;
@@ -34,6 +37,13 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     CK(cudaMemcpy(db, hb.data(), NOUT * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgam, hg.data(), NOUT * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dbet, hz.data(), NOUT * 4, cudaMemcpyHostToDevice));
+    __nv_bfloat16* dx0b = nullptr;
+    if (x0bf) {
+        std::vector<__nv_bfloat16> hb0((size_t)c0 * Np, __float2bfloat16(0.f));
+        for (int k = 0; k < c0; ++k) for (int p = 0; p < N; ++p) hb0[(size_t)k * Np + p] = __float2bfloat16(hx[(size_t)k * N + p]);
+        CK(cudaMalloc(&dx0b, hb0.size() * 2));
+        CK(cudaMemcpy(dx0b, hb0.data(), hb0.size() * 2, cudaMemcpyHostToDevice));
+    }
     unsigned* hdbg; CK(cudaHostAlloc(&hdbg, (148 * 16 + 7 * 64) * 4, cudaHostAllocMapped));
     memset(hdbg, 0, (148 * 16 + 7 * 64) * 4);
     unsigned* ddbg; CK(cudaHostGetDevicePointer(&ddbg, hdbg, 0));
@@ -41,16 +51,18 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     std::vector<float> hgp((size_t)(K - c0) * 2 * N), hgs(2 * K, 0.7f), hgh(2 * K, 0.1f);
     for (auto& v : hgp) v = (rand() / (float)RAND_MAX) * 4 - 2;
     float *dgs, *dgh; __nv_bfloat16* dgp;
-    std::vector<__nv_bfloat16> hgpb(hgp.size());
-    for (size_t i = 0; i < hgp.size(); ++i) { hgpb[i] = __float2bfloat16(hgp[i]); hgp[i] = __bfloat162float(hgpb[i]); }
-    CK(cudaMalloc(&dgp, hgp.size() * 2)); CK(cudaMalloc(&dgs, hgs.size() * 4)); CK(cudaMalloc(&dgh, hgh.size() * 4));
-    CK(cudaMemcpy(dgp, hgpb.data(), hgp.size() * 2, cudaMemcpyHostToDevice));
+    const size_t gch = (size_t)(K - c0) * 2;
+    std::vector<__nv_bfloat16> hgpb(gch * Np, __float2bfloat16(0.f));
+    for (size_t c = 0; c < gch; ++c) for (int p = 0; p < N; ++p) { __nv_bfloat16 b = __float2bfloat16(hgp[c * N + p]); hgpb[c * Np + p] = b; hgp[c * N + p] = __bfloat162float(b); }
+    CK(cudaMalloc(&dgp, hgpb.size() * 2)); CK(cudaMalloc(&dgs, hgs.size() * 4)); CK(cudaMalloc(&dgh, hgh.size() * 4));
+    CK(cudaMemcpy(dgp, hgpb.data(), hgpb.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgs, hgs.data(), hgs.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dgh, hgh.data(), hgh.size() * 4, cudaMemcpyHostToDevice));
     tc::GemmParams P; memset(&P, 0, sizeof(P));
     P.seg.src[0] = dx; P.seg.src[1] = dx + (size_t)c0 * N; P.seg.src[2] = dx + (size_t)(c0 + c1) * N;
     P.seg.cend[0] = c0; P.seg.cend[1] = c0 + c1; P.seg.cend[2] = K;
-    P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = 0; P.seg.plane = N; P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
+    P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = 0; P.seg.plane[0] = P.seg.plane[1] = P.seg.plane[2] = N; P.seg.gate_plane = Np; P.seg.gate_seg = -1;
+    if (x0bf) { P.seg.src[0] = dx0b; P.seg.kind[0] = 1; P.seg.plane[0] = Np; } P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
     const int gseg = (K - c0 - c1 > 0) ? 2 : 1; const int glen = (gseg == 2) ? K - c0 - c1 : c1; const int gk0 = K - glen;
     if (gated) { P.seg.gate_seg = gseg; P.seg.gate_ch0 = glen; P.seg.gate_pre = dgp; P.seg.gate_scale = dgs; P.seg.gate_shift = dgh; }
     P.w_ks = 1; P.nrow1 = 1 << 30; P.nbias = NOUT; P.nout_store = NOUT; P.nstat = NOUT / 32;
@@ -58,11 +70,12 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     int ntiles = (N + 127) / 128, grid = ntiles < 148 ? ntiles : 148;
     P.sink = StatSink{dpart, dtot, dcnt, NOUT / 32, 4096};
     P.aff = AffineOut{dsc, dsh, dgam, dbet, NOUT, 32, 32.0 * N, 1e-5f};
-    int ns = 0; size_t smem = tc::gemm_smem_bytes(NOUT, K, &ns);
-    P.nstage = ns; int cols = 32; while (cols < 2 * NOUT) cols <<= 1; P.tmem_cols = cols; P.dbg = ddbg;
+    size_t smem = tc::plan_launch(P, 0, (mode & 1) != 0);
+    P.reverse = (mode & 2) ? 1 : 0; P.dbg = ddbg;
+    const int ns = P.nstage, cols = P.tmem_cols;
     CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
     CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
-    printf("grid=%d smem=%zu nstage=%d tmem_cols=%d\n", grid, smem, ns, cols); fflush(stdout);
+    printf("grid=%d smem=%zu bulk=%d nraw=%d na=%d nstage=%d tmem_cols=%d\n", grid, smem, P.bulk, P.nraw, P.na, ns, cols); fflush(stdout);
     cudaEvent_t ev; CK(cudaEventCreate(&ev));
     if (gated) tc::gemm_gn_kernel<true, 0><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false, 0><<<grid, tc::NTHREADS, smem>>>(P);
     CK(cudaGetLastError());
@@ -122,17 +135,29 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false) {
     return bad ? 1 : 0;
 }
 
-int main() {
+int main(int argc, char** argv) {
     int rc = 0;
+    const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    // bulk producers (mode 1), + reverse (3), + bf16 first segment (5, 7); simt fallback (0) and unaligned shapes
     rc |= run(128, 80, 256, 16, 64);
+    rc |= run(128, 80, 256, 16, 64, false, 5);
     rc |= run(64, 80, 256, 16, 64, true);
-    rc |= run(96, 288, 62500, 96, 96, true);
+    rc |= run(64, 80, 256, 16, 64, true, 0);
     rc |= run(128, 80, 100, 16, 64);
-    rc |= run(64, 64, 128 * 5, 0, 0);
-    rc |= run(192, 288, 128 * 300, 96, 96);
+    rc |= run(128, 80, 100, 16, 64, false, 7);
+    rc |= run(64, 64, 128 * 5, 0, 0, false, 3);
+    rc |= run(32, 3, 128 * 7 + 12, 0, 0);
+    rc |= run(32, 63, 128 * 9 + 4, 0, 0);
+    rc |= run(192, 288, 128 * 300, 96, 96, false, 7);
+    rc |= run(96, 288, 62500, 96, 96, true, 3);
     rc |= run(96, 200, 15625, 8, 96);
     rc |= run(192, 192, 15625, 0, 96);
-    rc |= run(128, 224, 250000, 96, 64);
-    rc |= run(64, 64, 250000, 0, 64, true);
+    if (quick) return rc;
+    rc |= run(192, 224, 250000, 96, 64, false, 5);
+    rc |= run(192, 224, 250000, 96, 64, false, 4);
+    rc |= run(64, 64, 250000, 0, 64, true, 3);
+    rc |= run(64, 64, 250000, 0, 64, true, 0);
+    rc |= run(192, 80, 250000, 16, 64, false, 5);
+    rc |= run(192, 80, 250000, 16, 64, false, 4);
     return rc;
 }

@@ -57,13 +57,21 @@ uint64_t urnn_launch_count(void) { return g_launches.load(); }
 
 size_t urnn_cgru_fwd_workspace_bytes(const urnn_cell_desc* d) {
     if (!d || d->F <= 0 || d->F % 32) return 0;
-    return cgru_fwd_fp32_workspace(d);
+    size_t a = cgru_fwd_fp32_workspace(d);
+#ifndef URNN_NO_TC
+    size_t b = cgru_fwd_bf16_workspace(d);
+    if (b > a) a = b;
+#endif
+    return a;
 }
 
 int urnn_cgru_fwd(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, void* stream) {
     URNN_TRY(check_cell(d, p, e, h, h_out));
     cudaStream_t st = (cudaStream_t)stream;
+#ifndef URNN_NO_TC
+    tc_reset_direction();
+#endif
     switch (d->math) {
         case URNN_MATH_FP32: return cgru_fwd_fp32(d, p, x, e, h, h_out, ws, ws_bytes, st);
 #ifndef URNN_NO_TC
@@ -93,6 +101,7 @@ int urnn_conv1x1_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, int3
     URNN_CHECK_ARG(pool == 1 || (reinterpret_cast<uintptr_t>(x) & 7) == 0, "conv1x1: pooled input must be 8-byte aligned");
     URNN_CHECK_ARG(x && w && b && y, "conv1x1: null pointer");
 #ifndef URNN_NO_TC
+    if (math == URNN_MATH_BF16 && Cout <= 256) tc_reset_direction();
     if (math == URNN_MATH_BF16 && Cout <= 256)
         return conv1x1_lrelu_fwd_tc(Cin, Cout, H, W, pool, slope, x, 0, w, Cin, b, nullptr, y, (cudaStream_t)stream);
 #endif
@@ -117,6 +126,7 @@ int urnn_deconv2x2_lrelu_fwd(int32_t Cin, int32_t Cout, int32_t H, int32_t W, fl
     URNN_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 7) == 0, "deconv2x2: output must be 8-byte aligned");
     URNN_CHECK_ARG(x && w && b && y, "deconv2x2: null pointer");
 #ifndef URNN_NO_TC
+    if (math == URNN_MATH_BF16) tc_reset_direction();
     if (math == URNN_MATH_BF16)
         return deconv2x2_lrelu_fwd_tc(Cin, Cout, H, W, slope, x, 0, w, b, nullptr, y, (cudaStream_t)stream);
 #endif
@@ -175,9 +185,11 @@ static int ed_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, EdPlan* pl)
         pl->dec[k] = urnn_cell_desc{pl->h[sc], pl->w[sc], cx, d->dec_gru[k], 1, URNN_CELL_DECODER, d->math, d->gn_eps};
     }
     Arena a(ws, ws_bytes);
-    for (int k = 0; k < 3; ++k) pl->s[k] = a.take<float>((size_t)d->enc_conv[k] * pl->h[k] * pl->w[k]);
-    pl->up3 = a.take<float>((size_t)d->dec_conv[0] * pl->h[1] * pl->w[1]);
-    pl->up2 = a.take<float>((size_t)d->dec_conv[1] * pl->h[0] * pl->w[0]);
+    // fp32 maps in fp32 mode; bf16 maps with planes padded to whole 128-pixel tiles in bf16 mode (never larger than this)
+    auto map_floats = [](int c, int h, int w) { size_t n = (size_t)h * w, np = (n + 127) / 128 * 128; return (size_t)c * (n > (np + 1) / 2 ? n : (np + 1) / 2); };
+    for (int k = 0; k < 3; ++k) pl->s[k] = a.take<float>(map_floats(d->enc_conv[k], pl->h[k], pl->w[k]));
+    pl->up3 = a.take<float>(map_floats(d->dec_conv[0], pl->h[1], pl->w[1]));
+    pl->up2 = a.take<float>(map_floats(d->dec_conv[1], pl->h[0], pl->w[0]));
     pl->feat = a.take<float>((size_t)16 * d->H * d->W);
     size_t cw = 0;
     for (int k = 0; k < 3; ++k) {
@@ -221,22 +233,25 @@ static int ed_step_impl(const urnn_ed_desc* d, const urnn_ed_params* p, const St
         __nv_bfloat16* sb[3] = {(__nv_bfloat16*)pl.s[0], (__nv_bfloat16*)pl.s[1], (__nv_bfloat16*)pl.s[2]};
         __nv_bfloat16 *up3 = (__nv_bfloat16*)pl.up3, *up2 = (__nv_bfloat16*)pl.up2;
         const float* cur = input; int cin = s1.cin;
+        long np[3];
+        for (int k = 0; k < 3; ++k) np[k] = tc_pad_plane((long)pl.h[k] * pl.w[k]);
+        tc_reset_direction();
         for (int k = 0; k < 3; ++k) {
             int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
             URNN_TRY(conv1x1_lrelu_fwd_tc(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, 0,
                                           k == 0 ? s1.w : p->enc_stem_w[k], k == 0 ? s1.w_ld : (long)cin,
-                                          k == 0 ? s1.b : p->enc_stem_b[k], sb[k], nullptr, st));
+                                          k == 0 ? s1.b : p->enc_stem_b[k], sb[k], nullptr, st, 0, np[k]));
             URNN_TRY(check_cell(&pl.enc[k], &p->enc_cell[k], nullptr, sin[k], sout[k]));
-            URNN_TRY(cgru_fwd_bf16(&pl.enc[k], &p->enc_cell[k], sb[k], 1, nullptr, sin[k], sout[k], pl.cell_ws, pl.cell_ws_bytes, st));
+            URNN_TRY(cgru_fwd_bf16(&pl.enc[k], &p->enc_cell[k], sb[k], 1, nullptr, sin[k], sout[k], pl.cell_ws, pl.cell_ws_bytes, st, np[k]));
             cur = sout[k]; cin = d->enc_gru[k];
         }
         URNN_TRY(cgru_fwd_bf16(&pl.dec[0], &p->dec_cell[0], nullptr, 0, sout[2], sin[3], sout[3], pl.cell_ws, pl.cell_ws_bytes, st));
         URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[0], d->dec_conv[0], pl.h[2], pl.w[2], sl, sout[3], 0, p->dec_stem_w[0],
-                                        p->dec_stem_b[0], up3, nullptr, st));
-        URNN_TRY(cgru_fwd_bf16(&pl.dec[1], &p->dec_cell[1], up3, 1, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, st));
+                                        p->dec_stem_b[0], up3, nullptr, st, np[1]));
+        URNN_TRY(cgru_fwd_bf16(&pl.dec[1], &p->dec_cell[1], up3, 1, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, st, np[1]));
         URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, sout[4], 0, p->dec_stem_w[1],
-                                        p->dec_stem_b[1], up2, nullptr, st));
-        URNN_TRY(cgru_fwd_bf16(&pl.dec[2], &p->dec_cell[2], up2, 1, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, st));
+                                        p->dec_stem_b[1], up2, nullptr, st, np[0]));
+        URNN_TRY(cgru_fwd_bf16(&pl.dec[2], &p->dec_cell[2], up2, 1, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, st, np[0]));
         URNN_TRY(conv1x1_lrelu_fwd_tc(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], 0, p->dec_stem_w[2], d->dec_gru[2],
                                       p->dec_stem_b[2], nullptr, pl.feat, st));
         return urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream);

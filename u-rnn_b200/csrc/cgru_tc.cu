@@ -15,6 +15,12 @@
 namespace urnn {
 
 static int g_num_sms = 0;
+// Sweep direction: consecutive kernels walk the grid in opposite directions so that a kernel starts on the data its
+// predecessor touched last (still in the 126 MB L2).  Entry points reset it, so a given call sequence is reproducible.
+static thread_local int g_dir = 0;
+void tc_reset_direction() { g_dir = 0; }
+static inline long pad_plane(long n) { return (n + tc::TILE_M - 1) / tc::TILE_M * tc::TILE_M; }
+long tc_pad_plane(long n) { return pad_plane(n); }
 
 template <bool GATED, int EPI>
 static int tc_launch_t(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st) {
@@ -44,13 +50,11 @@ int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
         URNN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const bool gated = P.seg.gate_seg >= 0;
-    int nstage = 0;
-    size_t smem = tc::gemm_smem_bytes(P.NOUT, P.K, &nstage);
+    static const bool bulk_env = !(getenv("URNN_BULK") && getenv("URNN_BULK")[0] == '0');
+    const size_t smem = tc::plan_launch(P, epi, bulk_env);
     if (smem == 0) { set_error("tc gemm: weights %dx%d do not fit in shared memory", P.NOUT, P.K); return URNN_E_UNSUPPORTED; }
-    P.nstage = nstage;
-    int cols = 32;
-    while (cols < 2 * P.NOUT) cols <<= 1;
-    P.tmem_cols = cols;
+    static const bool rev_env = !(getenv("URNN_REVERSE") && getenv("URNN_REVERSE")[0] == '0');
+    P.reverse = rev_env ? g_dir : 0; g_dir ^= 1;
     P.dbg = nullptr;
     int ntiles = (P.N + tc::TILE_M - 1) / tc::TILE_M;
     int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
@@ -66,7 +70,8 @@ int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
 
 void tc_params_defaults(tc::GemmParams& P) {
     P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
-    for (int i = 0; i < 3; ++i) { P.seg.src[i] = nullptr; P.seg.cend[i] = 0; P.seg.kind[i] = 0; }
+    for (int i = 0; i < 3; ++i) { P.seg.src[i] = nullptr; P.seg.cend[i] = 0; P.seg.kind[i] = 0; P.seg.plane[i] = 0; }
+    P.seg.gate_plane = 0; P.bulk = 0; P.nraw = 0; P.na = 0; P.reverse = 0; P.nstage = 0;
     P.w_ks = 1; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0; P.bias = nullptr; P.nbias = 0;
     P.out = nullptr; P.out_f32 = nullptr; P.addend = nullptr; P.nstat = 0; P.slope = 0.f; P.img_w = 0; P.n_base = 0;
     P.sink = StatSink{nullptr, nullptr, nullptr, 0, 0, CommDev{1, 0, {nullptr}, {nullptr}, nullptr}};
@@ -77,65 +82,89 @@ void tc_params_defaults(tc::GemmParams& P) {
 // ------------------------------------------------------------------------------------------------ stems on tcgen05
 // y = [AvgPool2](LeakyReLU(conv1x1(x) + b)); x fp32 (kind 0) or bf16 (kind 1); exactly one of y_bf16 / y_f32 is set
 int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope, const void* x, int xkind,
-                         const float* w, long w_ld, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st) {
+                         const float* w, long w_ld, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st,
+                         long x_plane, long y_plane) {
+    if (x_plane == 0) x_plane = (long)H * W;
     if (Cout > 256) { set_error("conv1x1(bf16): Cout=%d > 256", Cout); return URNN_E_UNSUPPORTED; }
     if (pool == 2 && xkind != 0) { set_error("conv1x1(bf16): pooled stem needs an fp32 source"); return URNN_E_UNSUPPORTED; }
     tc::GemmParams P; tc_params_defaults(P);
     P.seg.src[0] = P.seg.src[1] = P.seg.src[2] = x; P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = xkind;
-    P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = Cin; P.seg.plane = (long)H * W;
+    P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = Cin; P.seg.plane[0] = P.seg.plane[1] = P.seg.plane[2] = x_plane;
     P.W = w; P.w_ld = w_ld; P.w_ks = 1; P.nrow1 = 1 << 30;
     P.bias = b; P.nbias = Cout; P.NOUT = (Cout + 31) & ~31; P.nout_store = Cout; P.K = Cin;
     P.out = y_bf16; P.out_f32 = y_f32; P.slope = slope;
-    if (pool == 1) { P.N = H * W; P.out_plane = (long)H * W; return tc_launch(P, tc::EPI_LRELU, st); }
-    P.N = 4 * (H / 2) * (W / 2); P.out_plane = (long)(H / 2) * (W / 2); P.img_w = W;
+    if (pool == 1) { P.N = H * W; P.out_plane = y_plane ? y_plane : (long)H * W; return tc_launch(P, tc::EPI_LRELU, st); }
+    P.N = 4 * (H / 2) * (W / 2); P.out_plane = y_plane ? y_plane : (long)(H / 2) * (W / 2); P.img_w = W;
     return tc_launch(P, tc::EPI_POOL, st);
 }
 
 // y = LeakyReLU(ConvTranspose2d(k2,s2)(x) + b): GEMM rows n = co*4 + dy*2 + dx, split into launches of <= 256 rows
 int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const void* x, int xkind, const float* w,
-                           const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st) {
+                           const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st, long y_plane) {
     const int M = 4 * Cout;
     int per = 256;
     if (M <= 256) per = (M + 31) & ~31; else if (M % 192 == 0) per = 192; else if (M % 128 == 0) per = 128;
     for (int n0 = 0; n0 < M; n0 += per) {
         tc::GemmParams P; tc_params_defaults(P);
         P.seg.src[0] = P.seg.src[1] = P.seg.src[2] = x; P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = xkind;
-        P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = Cin; P.seg.plane = (long)H * W;
+        P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = Cin; P.seg.plane[0] = P.seg.plane[1] = P.seg.plane[2] = (long)H * W;
         P.W = w + n0; P.w_ld = 1; P.w_ks = M; P.nrow1 = 1 << 30;
         P.bias = b; P.NOUT = per; P.nout_store = (M - n0 < per) ? (M - n0) : per; P.K = Cin; P.N = H * W;
-        P.out = y_bf16; P.out_f32 = y_f32; P.out_plane = (long)4 * H * W; P.slope = slope; P.img_w = W; P.n_base = n0;
+        P.out = y_bf16; P.out_f32 = y_f32; P.out_plane = y_plane ? y_plane : (long)4 * H * W; P.slope = slope; P.img_w = W; P.n_base = n0;
         URNN_TRY(tc_launch(P, tc::EPI_DECONV, st));
     }
     return URNN_OK;
 }
 
-// h' = (1-z)*h + z*tanh(GN2(C)),  z = sigmoid(GN1(G)[:F]); G and C are bf16 maps, flat over (channel, pixel)
+// h' = (1-z)*h + z*tanh(GN2(C)),  z = sigmoid(GN1(G)[:F]); G and C are bf16 maps with padded planes.
+// Pixel-major like the GEMM sweeps: blockIdx.y = block of 256*VEC pixels, blockIdx.x = group of BLEND_CH channels.
+constexpr int BLEND_CH = 8;
+template <int VEC>
 __global__ void __launch_bounds__(256)
 cgru_blend_bf16_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ C,
                        const float* __restrict__ h, const float* __restrict__ sc1, const float* __restrict__ sh1,
                        const float* __restrict__ sc2, const float* __restrict__ sh2, float* __restrict__ h_out,
-                       long N, long nquad) {
+                       long N, long gplane, int F, int reverse) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nquad) return;
-    const uint2 gw = __ldg(reinterpret_cast<const uint2*>(G) + idx);
-    const uint2 cw = __ldg(reinterpret_cast<const uint2*>(C) + idx);
-    const float4 hv = __ldg(reinterpret_cast<const float4*>(h) + idx);
-    float gv[4], cv[4];
-    tc::unpack_bf16x2(gw.x, gv[0], gv[1]); tc::unpack_bf16x2(gw.y, gv[2], gv[3]);
-    tc::unpack_bf16x2(cw.x, cv[0], cv[1]); tc::unpack_bf16x2(cw.y, cv[2], cv[3]);
-    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
-    float o[4];
-    const int c0 = (int)((idx * 4) / N), c3 = (int)((idx * 4 + 3) / N);
+    const long pb = reverse ? (long)(gridDim.y - 1 - blockIdx.y) : (long)blockIdx.y;
+    const long p = (pb * 256 + threadIdx.x) * VEC;
+    if (p >= N) return;
+    const int c0 = blockIdx.x * BLEND_CH;
+    float gv[BLEND_CH][VEC], cv[BLEND_CH][VEC], hv[BLEND_CH][VEC];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int c = (c0 == c3) ? c0 : (int)((idx * 4 + u) / N);
-        const float a1 = __ldg(sc1 + c), b1 = __ldg(sh1 + c), a2 = __ldg(sc2 + c), b2 = __ldg(sh2 + c);
-        const float z = sigmoid_acc(fmaf(gv[u], a1, b1)), t = tanhf(fmaf(cv[u], a2, b2));
-        o[u] = (1.f - z) * hh[u] + z * t;
+    for (int j = 0; j < BLEND_CH; ++j) {
+        const int c = c0 + j;
+        if (c < F) {
+            if constexpr (VEC == 4) {
+                const uint2 gw = __ldg(reinterpret_cast<const uint2*>(G + (long)c * gplane + p));
+                const uint2 cw = __ldg(reinterpret_cast<const uint2*>(C + (long)c * gplane + p));
+                const float4 hh = __ldg(reinterpret_cast<const float4*>(h + (long)c * N + p));
+                tc::unpack_bf16x2(gw.x, gv[j][0], gv[j][1]); tc::unpack_bf16x2(gw.y, gv[j][2], gv[j][3]);
+                tc::unpack_bf16x2(cw.x, cv[j][0], cv[j][1]); tc::unpack_bf16x2(cw.y, cv[j][2], cv[j][3]);
+                hv[j][0] = hh.x; hv[j][1] = hh.y; hv[j][2] = hh.z; hv[j][3] = hh.w;
+            } else {
+                gv[j][0] = __bfloat162float(G[(long)c * gplane + p]);
+                cv[j][0] = __bfloat162float(C[(long)c * gplane + p]);
+                hv[j][0] = __ldg(h + (long)c * N + p);
+            }
+        }
     }
-    reinterpret_cast<float4*>(h_out)[idx] = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int j = 0; j < BLEND_CH; ++j) {
+        const int c = c0 + j;
+        if (c < F) {
+            const float a1 = __ldg(sc1 + c), b1 = __ldg(sh1 + c), a2 = __ldg(sc2 + c), b2 = __ldg(sh2 + c);
+            float o[VEC];
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                const float z = sigmoid_acc(fmaf(gv[j][u], a1, b1)), t = tanhf(fmaf(cv[j][u], a2, b2));
+                o[u] = (1.f - z) * hv[j][u] + z * t;
+            }
+            if constexpr (VEC == 4) *reinterpret_cast<float4*>(h_out + (long)c * N + p) = make_float4(o[0], o[1], o[2], o[3]);
+            else h_out[(long)c * N + p] = o[0];
+        }
+    }
 }
 
 struct CellWsBf16 {
@@ -155,20 +184,24 @@ static size_t cell_ws_bf16(const urnn_cell_desc* d, void* ws, size_t ws_bytes, C
     w.scale2 = a.take<float>(F);     w.shift2 = a.take<float>(F);
     w.partial1 = a.take<float2>((size_t)(2 * F / 32) * gx);
     w.partial2 = a.take<float2>((size_t)(F / 32) * gx);
-    w.GP = a.take<__nv_bfloat16>((size_t)3 * F * N);
-    w.C = a.take<__nv_bfloat16>((size_t)F * N);
+    const size_t Np = (size_t)pad_plane(N);            // bf16 planes are padded to whole 128-pixel tiles (bulk copies)
+    w.GP = a.take<__nv_bfloat16>((size_t)3 * F * Np);
+    w.C = a.take<__nv_bfloat16>((size_t)F * Np);
     if (out) *out = w;
     return align_up(a.off, 256);
 }
 
+size_t cgru_fwd_bf16_workspace(const urnn_cell_desc* d) { return cell_ws_bf16(d, nullptr, 0, nullptr); }
+
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
-                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st, long x_plane) {
     if (d->ksize != 1) {                                                                 // k>1: fp32 taps path
         if (xkind != 0) { set_error("cgru_fwd: bf16 x needs k=1"); return URNN_E_UNSUPPORTED; }
         return cgru_fwd_fp32(d, p, (const float*)x, e, h, h_out, ws, ws_bytes, st);
     }
     const int F = d->F;
-    const long N = (long)d->H * d->W;
+    const long N = (long)d->H * d->W, Np = pad_plane(N);
+    if (x_plane == 0) x_plane = N;
     const int Ch = (d->variant == URNN_CELL_DECODER) ? 2 * F : F;
     const int Ktot = d->Cx + Ch;
     const int Cx_eff = x ? d->Cx : 0;
@@ -184,15 +217,15 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
 
     tc::GemmParams P; tc_params_defaults(P);
     // segments [x | e | h]; missing ones get zero width
-    int n = 0; const void* srcs[3] = {h, h, h}; int cnt[3] = {0, 0, 0}; int kinds[3] = {0, 0, 0};
-    if (x) { srcs[n] = x; cnt[n] = d->Cx; kinds[n] = xkind; ++n; }
+    int n = 0; const void* srcs[3] = {h, h, h}; int cnt[3] = {0, 0, 0}; int kinds[3] = {0, 0, 0}; long planes[3] = {N, N, N};
+    if (x) { srcs[n] = x; cnt[n] = d->Cx; kinds[n] = xkind; planes[n] = x_plane; ++n; }
     if (d->variant == URNN_CELL_DECODER) { srcs[n] = e; cnt[n] = F; ++n; }
     srcs[n] = h; cnt[n] = F; const int hseg = n; ++n;
     int acc = 0;
-    for (int i = 0; i < 3; ++i) { P.seg.src[i] = srcs[i]; P.seg.kind[i] = kinds[i]; acc += cnt[i]; P.seg.cend[i] = acc; }
-    P.seg.plane = N;
+    for (int i = 0; i < 3; ++i) { P.seg.src[i] = srcs[i]; P.seg.kind[i] = kinds[i]; P.seg.plane[i] = planes[i]; acc += cnt[i]; P.seg.cend[i] = acc; }
+    P.seg.gate_plane = Np;
     P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
-    P.N = (int)N; P.K = Keff; P.out_plane = N; P.addend = nullptr;
+    P.N = (int)N; P.K = Keff; P.out_plane = Np; P.addend = nullptr;
 
     // ---- sweep A
     P.W = p->w1 + aoff; P.w_ld = Ktot; P.nrow1 = 2 * F;
@@ -210,10 +243,11 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     P.seg.gate_ch0 = F; P.seg.gate_pre = w.GP; P.seg.gate_scale = w.scale1; P.seg.gate_shift = w.shift1;
     if (split) {
         P.seg.src[0] = P.seg.src[1] = P.seg.src[2] = h; P.seg.kind[0] = P.seg.kind[1] = P.seg.kind[2] = 0;
+        P.seg.plane[0] = P.seg.plane[1] = P.seg.plane[2] = N;
         P.seg.cend[0] = P.seg.cend[1] = P.seg.cend[2] = F;
         P.seg.gate_seg = 0;
         P.K = F; P.W = p->w2 + aoff + Kxe;
-        P.addend = w.GP + (size_t)2 * F * N;
+        P.addend = w.GP + (size_t)2 * F * Np;
     } else {
         P.seg.gate_seg = hseg;
         P.W = p->w2 + aoff;
@@ -225,18 +259,27 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     URNN_TRY(tc_launch(P, tc::EPI_GN, st));
 
     // ---- sweep C
-    const long nquad = (long)F * N / 4;
     {
         static const bool pdl = !(getenv("URNN_PDL") && getenv("URNN_PDL")[0] == '0');
+        const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0;
+        const long per = vec ? 1024 : 256;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((nquad + 255) / 256)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cfg.gridDim = dim3((unsigned)((F + BLEND_CH - 1) / BLEND_CH), (unsigned)((N + per - 1) / per));
+        cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        URNN_CHECK_ARG(cfg.gridDim.y <= 65535u, "cgru_fwd(bf16): grid of %ld cells too large for the blend sweep", N);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-        URNN_CUDA(cudaLaunchKernelEx(&cfg, cgru_blend_bf16_kernel, (const __nv_bfloat16*)w.GP, (const __nv_bfloat16*)w.C, h,
-                                     (const float*)w.scale1, (const float*)w.shift1, (const float*)w.scale2,
-                                     (const float*)w.shift2, h_out, N, nquad));
+        const int rev = g_dir; g_dir ^= 1;
+        if (vec)
+            URNN_CUDA(cudaLaunchKernelEx(&cfg, cgru_blend_bf16_kernel<4>, (const __nv_bfloat16*)w.GP, (const __nv_bfloat16*)w.C, h,
+                                         (const float*)w.scale1, (const float*)w.shift1, (const float*)w.scale2,
+                                         (const float*)w.shift2, h_out, N, Np, F, rev));
+        else
+            URNN_CUDA(cudaLaunchKernelEx(&cfg, cgru_blend_bf16_kernel<1>, (const __nv_bfloat16*)w.GP, (const __nv_bfloat16*)w.C, h,
+                                         (const float*)w.scale1, (const float*)w.shift1, (const float*)w.scale2,
+                                         (const float*)w.shift2, h_out, N, Np, F, rev));
     }
     URNN_LAUNCH_CHECK();
     return URNN_OK;

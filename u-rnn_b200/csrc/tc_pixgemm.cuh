@@ -15,9 +15,15 @@
 // successive 128-pixel tiles overlap; producers additionally keep the loads of the next ring slot in flight
 // while converting the current one.  Weights are converted once per CTA and stay resident in shared memory.
 //
-// Why no TMA for the activations: they must be rounded fp32 -> bf16 (and, for the candidate GEMM, multiplied by
-// the reset gate) before the tensor core sees them.  The producer is therefore SIMT and publishes its shared
-// stores to the async proxy with fence.proxy.async.
+// Activations must be rounded fp32 -> bf16 (and, for the candidate GEMM, multiplied by the reset gate) before the
+// tensor core sees them, so a SIMT stage always sits between HBM and the MMA operand.  Two producer modes:
+//   bulk (default whenever every source plane is 16-byte aligned): warp 25 streams the raw fp32 / bf16 channel rows
+//        of a unit (32 channels x 128 pixels) into a staging ring with 1-D TMA bulk copies (cp.async.bulk +
+//        mbarrier complete_tx) -- up to 6 units (96 KB) in flight per SM with no register or LSU cost -- and
+//        warps 8-23 only convert staging -> swizzled bf16 operand (shared -> shared).  Their fence.proxy.async
+//        (MEMBAR.ALL.CTA) then has no global loads to wait for.
+//   simt (fallback for unaligned planes, e.g. 125 x 125 maps, and the 2x2 pooling gather): warps 8-23 load from
+//        global memory themselves (64-channel units).
 #pragma once
 #include <cuda_bf16.h>
 #include "urnn_common.cuh"
@@ -30,8 +36,15 @@ constexpr int KBLK = 64;              // channels per ring slot
 constexpr int STAGE_BYTES = TILE_M * KBLK * 2;
 constexpr int NPROD = 512;            // producer threads
 constexpr int NEPI = 256;             // epilogue threads: warp w owns TMEM lanes 32*(w%4).. and column groups w/4, w/4+2, ..
-constexpr int NTHREADS = NEPI + NPROD + 32;
+constexpr int NTHREADS = NEPI + NPROD + 64;
 constexpr int MMA_WARP = (NEPI + NPROD) / 32;
+constexpr int TMA_WARP = MMA_WARP + 1;      // bulk mode: issues the cp.async.bulk row copies
+constexpr int UNIT_K = 32;            // bulk mode: channels per unit
+constexpr int RAW_ROW = 512;          // bulk mode: staging bytes per channel row (128 fp32; bf16 rows use the first 256)
+constexpr int RAW_SLOT = UNIT_K * RAW_ROW;            // 16 KB
+constexpr int GRAW_SLOT = UNIT_K * 256;               // reset-gate pre-activations (bf16) of a unit
+constexpr int A_SLOT_BULK = TILE_M * UNIT_K * 2;      // 8 KB operand slot
+constexpr int MAX_RAW = 6, MAX_ASLOT = 4;
 constexpr int MAXG = 8;               // NOUT <= 256 -> at most 8 groups of 32 output channels
 constexpr int MAXKB = 5;              // K <= 320 channels per contraction
 constexpr size_t SMEM_CAP = 229376;   // dynamic shared memory budget (227 KB opt-in limit minus static use)
@@ -54,6 +67,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D TMA bulk copy global -> shared; completion is signalled on `bar` as `bytes` of transaction count.
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -108,10 +130,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 }
 // MN-major (pixel-contiguous) A tile, 128-byte swizzle: 1024-byte atoms of 8 K-rows x 64 MN elements;
 // leading byte offset = distance between atoms along MN (8192), stride byte offset = along K (1024).
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo = 8192) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(lbo >> 4) << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
@@ -168,7 +190,8 @@ __device__ __forceinline__ void load8(const void* base, int kind, long off, int 
 // gate_pre is a bf16 map).
 struct Segs {
     const void* src[3]; int cend[3]; int kind[3];
-    long plane;
+    long plane[3];                  // elements between channel planes of each map (>= N; internal bf16 maps are padded)
+    long gate_plane;                // same for gate_pre
     int gate_seg; int gate_ch0;
     const __nv_bfloat16* gate_pre; const float* gate_scale; const float* gate_shift;
 };
@@ -190,7 +213,9 @@ struct GemmParams {
     int img_w;                               // EPI_POOL: input width (producer gathers 2x2 quads); EPI_DECONV: input width
     int n_base;                              // EPI_DECONV: global column offset of this launch (n = co*4 + dy*2 + dx)
     StatSink sink; AffineOut aff;
-    int nstage;                              // K-block ring depth
+    int nstage;                              // simt mode: K-block ring depth (64-channel slots)
+    int bulk, nraw, na;                      // bulk mode: on/off, staging ring depth, operand ring depth (32-channel slots)
+    int reverse;                             // walk the tiles from the last to the first (L2 reuse between sweeps)
     int tmem_cols;                           // power of two >= 2 * NOUT
     volatile unsigned* dbg;                  // optional host-mapped progress / trace words (bring-up only)
 };
@@ -229,15 +254,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const int nkb = (Kp + KBLK - 1) / KBLK;                 // K blocks per tile
     const int last_k = Kp - (nkb - 1) * KBLK;               // valid (padded) channels in the last block
     const int wblk_bytes = NOUT * 128;
+    const bool bulk = P.bulk != 0;
+    const int nslot = bulk ? P.na : P.nstage;               // operand ring depth (8 KB slots in bulk mode, 16 KB otherwise)
+    const int nu = (Kp + UNIT_K - 1) / UNIT_K;              // bulk mode: 32-channel units per tile
+    const uint32_t raw_slot_bytes = GATED ? (RAW_SLOT + GRAW_SLOT) : RAW_SLOT;
     const uint32_t w_off = 0;
     const uint32_t a_off = w_off + (uint32_t)nkb * wblk_bytes;
-    const uint32_t bias_off = a_off + (uint32_t)P.nstage * STAGE_BYTES;
+    const uint32_t raw_off = a_off + (uint32_t)(bulk ? P.na * A_SLOT_BULK : P.nstage * STAGE_BYTES);
+    const uint32_t bias_off = raw_off + (bulk ? (uint32_t)P.nraw * raw_slot_bytes : 0u);
     const uint32_t bar_off = bias_off + 1024;
     const uint32_t tab_off = bar_off + 512;                  // per-channel source table: MAXKB*64 entries of 32 bytes
-    // barriers: full[nstage], empty[nstage], tmem_full[2], tmem_empty[2]
-    const uint32_t full0 = base + bar_off, empty0 = full0 + 8 * P.nstage;
-    const uint32_t tfull0 = empty0 + 8 * P.nstage, tempty0 = tfull0 + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + bar_off + 16 * P.nstage + 32);
+    // barriers: full[8], empty[8], tmem_full[2], tmem_empty[2], (tmem slot), raw_full[8], raw_empty[8]
+    const uint32_t full0 = base + bar_off, empty0 = full0 + 64;
+    const uint32_t tfull0 = empty0 + 64, tempty0 = tfull0 + 16;
+    const uint32_t rfull0 = base + bar_off + 256, rempty0 = rfull0 + 64;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + bar_off + 176);
     float* sbias = reinterpret_cast<float*>(sm + bias_off);
     struct ChanEnt { const char* ptr; const char* gptr; float sc, sh; int meta; int pad; };   // meta: 1 valid, 2 bf16, 4 gated
     ChanEnt* ctab = reinterpret_cast<ChanEnt*>(sm + tab_off);
@@ -247,7 +278,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
     if (tid == 0) {
-        for (int s = 0; s < P.nstage; ++s) { mbar_init(full0 + 8 * s, NPROD / 2); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < nslot; ++s) { mbar_init(full0 + 8 * s, NPROD / 2); mbar_init(empty0 + 8 * s, 1); }
+        if (bulk) for (int s = 0; s < P.nraw; ++s) { mbar_init(rfull0 + 8 * s, 1); mbar_init(rempty0 + 8 * s, NPROD / 2); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NEPI); }
         fence_barrier_init();
     }
@@ -280,10 +312,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             const Segs& S = P.seg;
             const int sg = (k < S.cend[0]) ? 0 : ((k < S.cend[1]) ? 1 : 2);
             const int cc = k - (sg == 0 ? 0 : S.cend[sg - 1]);
-            e.ptr = reinterpret_cast<const char*>(S.src[sg]) + (long)cc * S.plane * (S.kind[sg] ? 2 : 4);
+            e.ptr = reinterpret_cast<const char*>(S.src[sg]) + (long)cc * S.plane[sg] * (S.kind[sg] ? 2 : 4);
             e.meta = 1 | (S.kind[sg] ? 2 : 0);
             if (GATED && sg == S.gate_seg) {
-                e.gptr = reinterpret_cast<const char*>(S.gate_pre) + (long)(S.gate_ch0 + cc) * S.plane * 2;
+                e.gptr = reinterpret_cast<const char*>(S.gate_pre) + (long)(S.gate_ch0 + cc) * S.gate_plane * 2;
                 e.meta |= 4 | ((S.gate_ch0 + cc) << 8);
             }
         }
@@ -328,8 +360,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         bool aligned = (N & 3) == 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-            aligned = aligned && ((reinterpret_cast<uintptr_t>(S.src[i]) & (S.kind[i] ? 7 : 15)) == 0);
-        if (GATED) aligned = aligned && ((reinterpret_cast<uintptr_t>(S.gate_pre) & 7) == 0);
+            aligned = aligned && ((reinterpret_cast<uintptr_t>(S.src[i]) & (S.kind[i] ? 7 : 15)) == 0) && ((S.plane[i] & 3) == 0);
+        if (GATED) aligned = aligned && ((reinterpret_cast<uintptr_t>(S.gate_pre) & 7) == 0) && ((S.gate_plane & 3) == 0);
         // chunk c lives 2 K-atoms (2048 B) after chunk c-1: channel ch0 + 16c
         const uint32_t soff0 = (uint32_t)((px8 >> 3) * 8192 + (ch0 >> 3) * 1024 + (ch0 & 7) * 128 + (((px8 & 7) ^ (ch0 & 7)) << 4));
         const ChanEnt* myent = ctab + ch0;
@@ -440,18 +472,120 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             if (warp == NEPI / 32 && kb == nkb - 1) { TC_TRACE(1, trace_i); ++trace_i; }
         };
 
-        Buf b;
-        for (long u = grp;; u += 2) {
-            const long ti = u / nkb;
-            const int kb = (int)(u - ti * nkb);
-            const long tile = blockIdx.x + ti * gridDim.x;
-            if (tile >= ntiles) break;
-            const int stage = (int)(u % P.nstage);
-            const uint32_t phase = (uint32_t)((u / P.nstage) & 1);
-            if (EPI != EPI_POOL && aligned && (tile + 1) * TILE_M <= N) issue_fast((int)tile, kb, b);
-            else issue_slow((int)tile, kb, b);
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            commit(kb, stage, b);
+        if (!bulk) {
+            Buf b;
+            for (long u = grp;; u += 2) {
+                const long ti = u / nkb;
+                const int kb = (int)(u - ti * nkb);
+                long tile = blockIdx.x + ti * gridDim.x;
+                if (tile >= ntiles) break;
+                if (P.reverse) tile = ntiles - 1 - tile;
+                const int stage = (int)(u % P.nstage);
+                const uint32_t phase = (uint32_t)((u / P.nstage) & 1);
+                if (EPI != EPI_POOL && aligned && (tile + 1) * TILE_M <= N) issue_fast((int)tile, kb, b);
+                else issue_slow((int)tile, kb, b);
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                commit(kb, stage, b);
+            }
+        } else {
+            // ---- bulk mode: staging (raw rows landed by TMA) -> bf16 swizzled operand slot.  Unit = 32 channels x 128
+            // pixels; a thread converts 8 pixels of channels ch0 and ch0 + 16.  Operand slot: 1024-byte atoms of 8 channels x
+            // 64 pixels, atom(mblk, kblk) at mblk*4096 + kblk*1024.
+            const uint32_t so[2] = {
+                (uint32_t)((px8 >> 3) * 4096 + (ch0 >> 3) * 1024 + (ch0 & 7) * 128 + (((px8 & 7) ^ (ch0 & 7)) << 4)),
+                (uint32_t)((px8 >> 3) * 4096 + ((ch0 + 16) >> 3) * 1024 + (ch0 & 7) * 128 + (((px8 & 7) ^ (ch0 & 7)) << 4))};
+            // fp32 rows: a thread's 32 bytes are fetched as two 16-byte pieces; odd groups of four threads fetch the
+            // upper piece first so that a quarter-warp touches all 32 banks (conflict-free LDS.128)
+            const bool swp = ((px8 >> 2) & 1) != 0;
+            for (long u = grp;; u += 2) {
+                const long ti = u / nu;
+                const int kb = (int)(u - ti * nu);
+                long tile = blockIdx.x + ti * gridDim.x;
+                if (tile >= ntiles) break;
+                if (P.reverse) tile = ntiles - 1 - tile;
+                const int rs = (int)(u % P.nraw), as = (int)(u % P.na);
+                const uint32_t rph = (uint32_t)((u / P.nraw) & 1), aph = (uint32_t)((u / P.na) & 1);
+                const long pbase = tile * TILE_M + px_off;
+                const int nv = (pbase >= N) ? 0 : ((N - pbase >= 8) ? 8 : (int)(N - pbase));   // valid pixels of my 8
+                const uint8_t* rawp = sm + raw_off + rs * raw_slot_bytes;
+                mbar_wait(rfull0 + 8 * rs, rph);
+                uint4 pk[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int ch = ch0 + 16 * c;
+                    const ChanEnt* e = ctab + kb * UNIT_K + ch;
+                    const int meta = e->meta;
+                    float v[8];
+                    pk[c] = make_uint4(0u, 0u, 0u, 0u);
+                    if (meta & 1) {
+                        if (meta & 2) {
+                            const uint4 w = *reinterpret_cast<const uint4*>(rawp + ch * RAW_ROW + px8 * 16);
+                            unpack_bf16x2(w.x, v[0], v[1]); unpack_bf16x2(w.y, v[2], v[3]);
+                            unpack_bf16x2(w.z, v[4], v[5]); unpack_bf16x2(w.w, v[6], v[7]);
+                        } else {
+                            const uint8_t* r = rawp + ch * RAW_ROW + px8 * 32;
+                            const float4 f0 = *reinterpret_cast<const float4*>(r + (swp ? 16 : 0));
+                            const float4 f1 = *reinterpret_cast<const float4*>(r + (swp ? 0 : 16));
+                            const float4 lo = swp ? f1 : f0, hi = swp ? f0 : f1;
+                            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+                        }
+                        if constexpr (GATED) {
+                            if (meta & 4) {
+                                const uint4 g = *reinterpret_cast<const uint4*>(rawp + RAW_SLOT + ch * 256 + px8 * 16);
+                                float gv[8];
+                                unpack_bf16x2(g.x, gv[0], gv[1]); unpack_bf16x2(g.y, gv[2], gv[3]);
+                                unpack_bf16x2(g.z, gv[4], gv[5]); unpack_bf16x2(g.w, gv[6], gv[7]);
+                                const float sc = e->sc, sh = e->sh;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) v[q] *= sigmoid_fast(fmaf(gv[q], sc, sh));
+                            }
+                        }
+                        if (nv < 8) {                        // last tile: rows beyond the map hold stale staging bytes
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = (q < nv) ? v[q] : 0.f;
+                        }
+                        pk[c] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    }
+                }
+                mbar_arrive(rempty0 + 8 * rs);               // staging slot consumed (values are in registers)
+                mbar_wait(empty0 + 8 * as, aph ^ 1);
+                uint8_t* st = sm + a_off + as * A_SLOT_BULK;
+                *reinterpret_cast<uint4*>(st + so[0]) = pk[0];
+                *reinterpret_cast<uint4*>(st + so[1]) = pk[1];
+                fence_proxy_async();                         // generic-proxy stores -> visible to tcgen05.mma
+                mbar_arrive(full0 + 8 * as);
+                if (warp == NEPI / 32 && kb == nu - 1) { TC_TRACE(1, trace_i); ++trace_i; }
+            }
+        }
+    } else if (warp == TMA_WARP) {
+        // =========================================================================== bulk-copy issuer (bulk mode)
+        // lane c streams channel c of every unit: one 512-byte (fp32) or 256-byte (bf16) row, plus the 256-byte row of
+        // reset-gate pre-activations for gated channels.
+        if (bulk) {
+            for (long u = 0;; ++u) {
+                const long ti = u / nu;
+                const int kb = (int)(u - ti * nu);
+                long tile = blockIdx.x + ti * gridDim.x;
+                if (tile >= ntiles) break;
+                if (P.reverse) tile = ntiles - 1 - tile;
+                const int rs = (int)(u % P.nraw);
+                const uint32_t rph = (uint32_t)((u / P.nraw) & 1);
+                const ChanEnt e = ctab[kb * UNIT_K + lane];
+                const long p0 = tile * TILE_M;
+                const int nvalid = (N - p0 >= TILE_M) ? TILE_M : (int)(N - p0);
+                // bf16 maps are internal and padded to whole tiles: always a full row.  fp32 maps: only the valid part
+                // (N % 4 == 0 is a precondition of bulk mode, so the size stays a multiple of 16).
+                uint32_t bytes = 0, gbytes = 0;
+                if (e.meta & 1) { bytes = (e.meta & 2) ? 256u : (uint32_t)nvalid * 4u; if (GATED && (e.meta & 4)) gbytes = 256u; }
+                const uint32_t total = __reduce_add_sync(0xffffffffu, bytes + gbytes);
+                mbar_wait(rempty0 + 8 * rs, rph ^ 1);
+                const uint32_t bar = rfull0 + 8 * rs;
+                if (lane == 0) mbar_arrive_expect_tx(bar, total);
+                __syncwarp();
+                const uint32_t dst = base + raw_off + rs * raw_slot_bytes;
+                if (bytes) bulk_g2s(dst + lane * RAW_ROW, e.ptr + p0 * ((e.meta & 2) ? 2 : 4), bytes, bar);
+                if (gbytes) bulk_g2s(dst + RAW_SLOT + lane * 256, e.gptr + p0 * 2, gbytes, bar);
+            }
         }
     } else if (warp == MMA_WARP) {
         // =========================================================================== MMA issuer
@@ -462,20 +596,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             mbar_wait(tempty0 + 8 * as, aphase ^ 1);         // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_stride);
-            for (int kb = 0; kb < nkb; ++kb) {
+            const int nunits = bulk ? nu : nkb;
+            for (int kb = 0; kb < nunits; ++kb) {
                 mbar_wait(full0 + 8 * stage, phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_addr = base + a_off + stage * STAGE_BYTES;
-                    const uint32_t b_addr = base + w_off + kb * wblk_bytes;
-                    const int nmma = ((kb == nkb - 1) ? last_k : KBLK) >> 4;
-                    for (int j = 0; j < nmma; ++j)
-                        umma_f16(d_tmem, smem_desc_mn_sw128(a_addr + j * 2048), smem_desc_sw128(b_addr + j * 32), idesc,
-                                 (kb | j) ? 1u : 0u);
+                    if (bulk) {
+                        const uint32_t a_addr = base + a_off + stage * A_SLOT_BULK;
+                        const uint32_t b_addr = base + w_off + (kb >> 1) * wblk_bytes + (kb & 1) * 64;
+                        const int left = (Kp - kb * UNIT_K) >> 4;
+                        const int nmma = left < 2 ? left : 2;
+                        for (int j = 0; j < nmma; ++j)
+                            umma_f16(d_tmem, smem_desc_mn_sw128(a_addr + j * 2048, 4096), smem_desc_sw128(b_addr + j * 32), idesc,
+                                     (kb | j) ? 1u : 0u);
+                    } else {
+                        const uint32_t a_addr = base + a_off + stage * STAGE_BYTES;
+                        const uint32_t b_addr = base + w_off + kb * wblk_bytes;
+                        const int nmma = ((kb == nkb - 1) ? last_k : KBLK) >> 4;
+                        for (int j = 0; j < nmma; ++j)
+                            umma_f16(d_tmem, smem_desc_mn_sw128(a_addr + j * 2048), smem_desc_sw128(b_addr + j * 32), idesc,
+                                     (kb | j) ? 1u : 0u);
+                    }
                     umma_commit(empty0 + 8 * stage);         // frees the ring slot when these MMAs retire
                 }
                 __syncwarp();
-                if (++stage == P.nstage) { stage = 0; phase ^= 1; }
+                if (++stage == nslot) { stage = 0; phase ^= 1; }
             }
             if (lane == 0) umma_commit(tfull0 + 8 * as);     // accumulator complete -> epilogue
             __syncwarp();
@@ -492,7 +637,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         const int ng = NOUT >> 5;
         const int lq = warp & 3, ghalf = warp >> 2;
         const int row = lq * 32 + lane;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int vt = blockIdx.x; vt < ntiles; vt += gridDim.x) {
+            const int tile = P.reverse ? ntiles - 1 - vt : vt;
             const long p = (long)tile * TILE_M + row;
             const bool valid = p < N;
             const float vmask = valid ? 1.f : 0.f;
@@ -514,7 +660,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             }
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
-            if (warp == 0) TC_TRACE(3, (tile - (int)blockIdx.x) / (int)gridDim.x);
+            if (warp == 0) TC_TRACE(3, (vt - (int)blockIdx.x) / (int)gridDim.x);
             const uint32_t t_addr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(as * acc_stride);
 #pragma unroll
             for (int gi = 0; gi < MAXG / 2; ++gi) {
@@ -591,7 +737,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             }
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * as);
-            if (warp == 0) TC_TRACE(4, (tile - (int)blockIdx.x) / (int)gridDim.x);
+            if (warp == 0) TC_TRACE(4, (vt - (int)blockIdx.x) / (int)gridDim.x);
             as ^= 1; if (as == 0) aphase ^= 1;
         }
         // per-CTA GroupNorm partials (fixed order: lanes -> lane quarters -> CTA)
@@ -618,15 +764,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
 }
 
 // dynamic shared memory needed for a given problem; 0 if it cannot fit
+static inline size_t gemm_smem_fixed(int NOUT, int K) {
+    const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
+    return 1024 /*align slack*/ + (size_t)nkb * NOUT * 128 + 1024 /*bias*/ + 512 /*barriers*/ + (size_t)nkb * KBLK * 32 /*source table*/;
+}
 static inline size_t gemm_smem_bytes(int NOUT, int K, int* nstage_out) {
     const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
-    const size_t fixed = 1024 /*align slack*/ + (size_t)nkb * NOUT * 128 + 1024 /*bias*/ + 512 /*barriers*/ + (size_t)nkb * KBLK * 32 /*source table*/;
+    const size_t fixed = gemm_smem_fixed(NOUT, K);
     const size_t cap = SMEM_CAP;
     if (fixed + 2 * STAGE_BYTES > cap || nkb > MAXKB) return 0;
     int ns = (int)((cap - fixed) / STAGE_BYTES);
     if (ns > 8) ns = 8;
     if (nstage_out) *nstage_out = ns;
     return fixed + (size_t)ns * STAGE_BYTES;
+}
+// bulk mode: operand ring (na slots of 8 KB) + staging ring (nraw slots of 16 KB, +8 KB each when gated); 0 if it cannot fit
+static inline size_t gemm_smem_bytes_bulk(int NOUT, int K, bool gated, int* nraw_out, int* na_out) {
+    const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
+    const size_t fixed = gemm_smem_fixed(NOUT, K);
+    if (nkb > MAXKB || fixed >= SMEM_CAP) return 0;
+    const size_t avail = SMEM_CAP - fixed, slot = (size_t)RAW_SLOT + (gated ? GRAW_SLOT : 0);
+    for (int na = 3; na >= 2; --na) {
+        if (avail < (size_t)na * A_SLOT_BULK + 2 * slot) continue;
+        int nraw = (int)((avail - (size_t)na * A_SLOT_BULK) / slot);
+        if (nraw > MAX_RAW) nraw = MAX_RAW;
+        if (na == 3 && nraw == MAX_RAW && avail >= (size_t)MAX_ASLOT * A_SLOT_BULK + (size_t)MAX_RAW * slot) na = MAX_ASLOT;
+        *nraw_out = nraw; *na_out = na;
+        return fixed + (size_t)na * A_SLOT_BULK + (size_t)nraw * slot;
+    }
+    return 0;
+}
+
+// Host side: choose the producer mode and ring depths for a filled-in GemmParams; returns the dynamic shared memory
+// size (0: the weights do not fit).  Bulk mode needs 16-byte aligned channel rows: fp32 maps with N % 4 == 0, bf16 maps
+// whose planes are padded to whole tiles (so a full 256-byte row is always in bounds).
+static inline size_t plan_launch(GemmParams& P, int epi, bool allow_bulk) {
+    const bool gated = P.seg.gate_seg >= 0;
+    bool bulk = allow_bulk && epi != EPI_POOL;
+    const long npad = ((long)P.N + TILE_M - 1) / TILE_M * TILE_M;
+    for (int i = 0; i < 3 && bulk; ++i) {
+        const int width = P.seg.cend[i] - (i ? P.seg.cend[i - 1] : 0);
+        if (width <= 0) continue;
+        const size_t esz = P.seg.kind[i] ? 2 : 4;
+        bulk = bulk && (reinterpret_cast<uintptr_t>(P.seg.src[i]) & 15) == 0 && ((size_t)P.seg.plane[i] * esz) % 16 == 0;
+        bulk = bulk && (P.seg.kind[i] ? (P.seg.plane[i] >= npad) : (P.N % 4 == 0));
+    }
+    if (bulk && gated)
+        bulk = (reinterpret_cast<uintptr_t>(P.seg.gate_pre) & 15) == 0 && (P.seg.gate_plane * 2) % 16 == 0 && P.seg.gate_plane >= npad;
+    int nstage = 0, nraw = 0, na = 0;
+    size_t smem = 0;
+    if (bulk) { smem = gemm_smem_bytes_bulk(P.NOUT, P.K, gated, &nraw, &na); if (smem == 0) bulk = false; }
+    if (!bulk) smem = gemm_smem_bytes(P.NOUT, P.K, &nstage);
+    P.nstage = nstage; P.bulk = bulk ? 1 : 0; P.nraw = nraw; P.na = na;
+    int cols = 32;
+    while (cols < 2 * P.NOUT) cols <<= 1;
+    P.tmem_cols = cols;
+    return smem;
 }
 
 }  // namespace tc

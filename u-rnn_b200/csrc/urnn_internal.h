@@ -23,12 +23,18 @@ int cgru_blend_launch(const CellWsView& w, const float* h, float* h_out, int F, 
 
 // tcgen05 bf16 path (cgru_tc.cu).  x / stem inputs may be fp32 (kind 0) or bf16 (kind 1) maps; stem outputs go
 // to exactly one of y_bf16 / y_f32.
+// x_plane / y_plane: elements between channel planes (0 = H*W); internal bf16 maps use tc_pad_plane(H*W) so that every
+// channel row of a 128-pixel tile is a 16-byte aligned, in-bounds TMA bulk copy.
+long tc_pad_plane(long n);
+void tc_reset_direction();
+size_t cgru_fwd_bf16_workspace(const urnn_cell_desc* d);
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
-                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                  const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st, long x_plane = 0);
 int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope, const void* x, int xkind,
-                         const float* w, long w_ld, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
+                         const float* w, long w_ld, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st,
+                         long x_plane = 0, long y_plane = 0);
 int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const void* x, int xkind, const float* w,
-                           const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st);
+                           const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st, long y_plane = 0);
 
 // fp32 FFMA path (urnn_fp32.cu)
 int cgru_fwd_fp32_passes(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
