@@ -36,6 +36,11 @@ UNIT = "cells*steps/s"
 H_DEF, W_DEF, HIST_DEF = 500, 500, 30
 
 
+def trace(msg):
+    if os.environ.get("URNN_BENCH_TRACE"):
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -47,6 +52,7 @@ def parse():
     ap.add_argument("--width", type=int, default=W_DEF)
     ap.add_argument("--hist", type=int, default=HIST_DEF)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=900, help="seconds before a stuck run dumps its stack and exits")
     ap.add_argument("--value-only", action="store_true", help="device-resident throughput only (large grids: skips the e2e / roofline legs)")
     return ap.parse_args()
 
@@ -219,10 +225,12 @@ def run_ours(a):
     def step(i):
         ops.ed_step_fwd(desc, params, xs_dev[i % ring], runner.states[i & 1], runner.states[(i & 1) ^ 1], out, runner.ws)
 
+    trace("built; warm-up")
     with torch.no_grad():
         for i in range(a.warmup):
             step(i)
         barrier()
+        trace("warm-up done; timed steps")
         n0 = lib.urnn_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
@@ -234,6 +242,7 @@ def run_ours(a):
         launches = lib.urnn_launch_count() - n0
     sec = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
     value = world * N * a.steps / sec
+    trace(f"value leg done: {sec / a.steps * 1e3:.3f} ms/step")
 
     if a.value_only:
         if rank == 0:
@@ -266,6 +275,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     sec_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e = world * N * a.steps / sec_e2e
+    trace("e2e leg done")
 
     # (2b) the reference's own workflow end to end (test.py:447-375): the event dict comes from the HOST once (3 static
     #      maps + the scalar rainfall series), inputs are assembled on the device every step (here: folded into the
@@ -281,6 +291,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     sec_ev = max_over_ranks(time.perf_counter() - t0)
     e2e_event = world * N * a.steps / sec_ev
+    trace("event leg done")
 
     # (3) roofline of the dominant op: the full-resolution decoder Skip-ConvGRU cell (36 % of the step's FLOPs and
     #     its largest kernels); algorithmic bytes = (C_x + C_e + C_d + F) * 4 per cell
@@ -300,6 +311,7 @@ def run_ours(a):
         c1.record()
         torch.cuda.synchronize()
     cell_sec = c0.elapsed_time(c1) * 1e-3 / reps
+    trace("roofline leg done")
     alg_bytes = (Cx + 2 * F + F) * 4 * N
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / cell_sec / 1e9
@@ -342,6 +354,9 @@ def run_ours(a):
 
 def main():
     a = parse()
+    # a wedged GPU must not hang the caller: dump the Python stack and exit instead
+    import faulthandler
+    faulthandler.dump_traceback_later(a.watchdog, exit=True)
     if a.impl == "reference":
         run_reference_arm(a)
     else:

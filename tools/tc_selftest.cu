@@ -16,10 +16,13 @@ using namespace urnn;
 static float bf16r(float f) { return __bfloat162float(__float2bfloat16(f)); }
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
-// mode bits: 1 = allow bulk producers, 2 = walk tiles in reverse, 4 = first segment is a bf16 map with padded planes
+// mode bits: 1 = allow bulk producers, 2 = walk tiles in reverse, 4 = first segment is a bf16 map with padded planes,
+// 8 = unpadded output planes (element-wise epilogue stores instead of staged 16-byte rows)
+static bool g_prof = false;
 int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1) {
     const long Np = ((long)N + 127) / 128 * 128;
     const bool x0bf = (mode & 4) && c0 > 0;
+    const long Op = (mode & 8) ? N : Np;              // output plane stride
     printf("== NOUT=%d K=%d N=%d segs=(%d,%d,%d) gated=%d mode=%d\n", NOUT, K, N, c0, c1, K - c0 - c1, (int)gated, mode); fflush(stdout);
     std::vector<float> hx((size_t)K * N), hw((size_t)NOUT * K), hb(NOUT), hg(NOUT, 1.f), hz(NOUT, 0.f);
     srand(1);
@@ -28,10 +31,10 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1
     for (auto& v : hb) v = (rand() / (float)RAND_MAX) - 0.5f;
     float *dx, *dw, *db, *dgam, *dbet, *dsc, *dsh; __nv_bfloat16* dout; float2* dpart; double2* dtot; unsigned* dcnt;
     CK(cudaMalloc(&dx, hx.size() * 4)); CK(cudaMalloc(&dw, hw.size() * 4)); CK(cudaMalloc(&db, NOUT * 4));
-    CK(cudaMalloc(&dout, (size_t)NOUT * N * 2)); CK(cudaMalloc(&dgam, NOUT * 4)); CK(cudaMalloc(&dbet, NOUT * 4));
+    CK(cudaMalloc(&dout, (size_t)NOUT * Op * 2)); CK(cudaMalloc(&dgam, NOUT * 4)); CK(cudaMalloc(&dbet, NOUT * 4));
     CK(cudaMalloc(&dsc, NOUT * 4)); CK(cudaMalloc(&dsh, NOUT * 4));
     CK(cudaMalloc(&dpart, 8 * 4096 * sizeof(float2))); CK(cudaMalloc(&dtot, 8 * sizeof(double2))); CK(cudaMalloc(&dcnt, 256));
-    CK(cudaMemset(dcnt, 0, 256)); CK(cudaMemset(dout, 0, (size_t)NOUT * N * 2));
+    CK(cudaMemset(dcnt, 0, 256)); CK(cudaMemset(dout, 0, (size_t)NOUT * Op * 2));
     CK(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db, hb.data(), NOUT * 4, cudaMemcpyHostToDevice));
@@ -66,7 +69,7 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1
     const int gseg = (K - c0 - c1 > 0) ? 2 : 1; const int glen = (gseg == 2) ? K - c0 - c1 : c1; const int gk0 = K - glen;
     if (gated) { P.seg.gate_seg = gseg; P.seg.gate_ch0 = glen; P.seg.gate_pre = dgp; P.seg.gate_scale = dgs; P.seg.gate_shift = dgh; }
     P.w_ks = 1; P.nrow1 = 1 << 30; P.nbias = NOUT; P.nout_store = NOUT; P.nstat = NOUT / 32;
-    P.W = dw; P.w_ld = K; P.bias = db; P.NOUT = NOUT; P.K = K; P.N = N; P.out = dout; P.out_plane = N;
+    P.W = dw; P.w_ld = K; P.bias = db; P.NOUT = NOUT; P.K = K; P.N = N; P.out = dout; P.out_plane = Op;
     int ntiles = (N + 127) / 128, grid = ntiles < 148 ? ntiles : 148;
     P.sink = StatSink{dpart, dtot, dcnt, NOUT / 32, 4096};
     P.aff = AffineOut{dsc, dsh, dgam, dbet, NOUT, 32, 32.0 * N, 1e-5f};
@@ -75,8 +78,14 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1
     const int ns = P.nstage, cols = P.tmem_cols;
     CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
     CK(cudaFuncSetAttribute(tc::gemm_gn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
-    printf("grid=%d smem=%zu bulk=%d nraw=%d na=%d nstage=%d tmem_cols=%d\n", grid, smem, P.bulk, P.nraw, P.na, ns, cols); fflush(stdout);
+    printf("grid=%d smem=%zu bulk=%d nraw=%d na=%d nstage=%d tmem_cols=%d out_vec=%d\n", grid, smem, P.bulk, P.nraw, P.na, ns, cols, P.out_vec); fflush(stdout);
     cudaEvent_t ev; CK(cudaEventCreate(&ev));
+    if (N >= 15000 && !g_prof) {                     // warm launch (weights in L2) so that the traced one shows the steady-state prologue
+        P.dbg = nullptr;
+        if (gated) tc::gemm_gn_kernel<true, 0><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false, 0><<<grid, tc::NTHREADS, smem>>>(P);
+        CK(cudaDeviceSynchronize());
+        P.dbg = ddbg;
+    }
     if (gated) tc::gemm_gn_kernel<true, 0><<<grid, tc::NTHREADS, smem>>>(P); else tc::gemm_gn_kernel<false, 0><<<grid, tc::NTHREADS, smem>>>(P);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev));
@@ -96,9 +105,9 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("kernel error: %s\n", cudaGetErrorString(e)); printf(" cta0:"); for (int i = 0; i < 15; ++i) printf(" %x", hdbg[i]); printf("\n"); return 2; }
-    std::vector<__nv_bfloat16> hob((size_t)NOUT * N); std::vector<float> ho((size_t)NOUT * N);
+    std::vector<__nv_bfloat16> hob((size_t)NOUT * Op); std::vector<float> ho((size_t)NOUT * N);
     CK(cudaMemcpy(hob.data(), dout, hob.size() * 2, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < ho.size(); ++i) ho[i] = __bfloat162float(hob[i]);
+    for (int n = 0; n < NOUT; ++n) for (int p = 0; p < N; ++p) ho[(size_t)n * N + p] = __bfloat162float(hob[(size_t)n * Op + p]);
     double maxerr = 0; long bad = 0;
     std::vector<float> xr(hx.size()), wr(hw.size());
     for (size_t i = 0; i < hx.size(); ++i) {
@@ -117,7 +126,7 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1
             if (d > 1e-3 + 8e-3 * fabs(a)) { if (bad < 5) printf("  mismatch n=%d p=%d ref=%f got=%f\n", n, p, a, ho[(size_t)n * N + p]); ++bad; }
         }
     printf("max abs err %.3e, mismatches %ld -> %s\n", maxerr, bad, bad ? "FAIL" : "ok"); fflush(stdout);
-    if (N >= 15000) {
+    if (N >= 15000 && !g_prof) {
         const unsigned* tr = hdbg + 148 * 16; unsigned t0 = tr[0];
         printf("trace (us since setup done): kernel entry %.1f kernel end %.1f\n", ((int)(tr[6 * 64] - t0)) * 1e-3, (tr[5 * 64] - t0) * 1e-3);
         for (int i = 0; i < 8; ++i)
@@ -138,13 +147,22 @@ int run(int NOUT, int K, int N, int c0, int c1, bool gated = false, int mode = 1
 int main(int argc, char** argv) {
     int rc = 0;
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    if (argc > 1 && !strcmp(argv[1], "prof")) {          // one launch per case, for ncu
+        g_prof = true;
+        rc |= run(192, 224, 250000, 96, 64, false, 5);
+        rc |= run(192, 224, 250000, 96, 64, false, 4);
+        rc |= run(64, 64, 250000, 0, 64, true, 3);
+        return rc;
+    }
     // bulk producers (mode 1), + reverse (3), + bf16 first segment (5, 7); simt fallback (0) and unaligned shapes
     rc |= run(128, 80, 256, 16, 64);
     rc |= run(128, 80, 256, 16, 64, false, 5);
     rc |= run(64, 80, 256, 16, 64, true);
     rc |= run(64, 80, 256, 16, 64, true, 0);
+    rc |= run(64, 80, 256, 16, 64, true, 9);
     rc |= run(128, 80, 100, 16, 64);
     rc |= run(128, 80, 100, 16, 64, false, 7);
+    rc |= run(128, 80, 100, 16, 64, false, 8);
     rc |= run(64, 64, 128 * 5, 0, 0, false, 3);
     rc |= run(32, 3, 128 * 7 + 12, 0, 0);
     rc |= run(32, 63, 128 * 9 + 4, 0, 0);

@@ -158,7 +158,7 @@ cgru_blend_bf16_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16*
             float o[VEC];
 #pragma unroll
             for (int u = 0; u < VEC; ++u) {
-                const float z = sigmoid_acc(fmaf(gv[j][u], a1, b1)), t = tanhf(fmaf(cv[j][u], a2, b2));
+                const float z = sigmoid_fast(fmaf(gv[j][u], a1, b1)), t = tanh_fast(fmaf(cv[j][u], a2, b2));
                 o[u] = (1.f - z) * hv[j][u] + z * t;
             }
             if constexpr (VEC == 4) *reinterpret_cast<float4*>(h_out + (long)c * N + p) = make_float4(o[0], o[1], o[2], o[3]);

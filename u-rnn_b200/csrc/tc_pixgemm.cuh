@@ -17,11 +17,12 @@
 //
 // Activations must be rounded fp32 -> bf16 (and, for the candidate GEMM, multiplied by the reset gate) before the
 // tensor core sees them, so a SIMT stage always sits between HBM and the MMA operand.  Two producer modes:
-//   bulk (default whenever every source plane is 16-byte aligned): warp 25 streams the raw fp32 / bf16 channel rows
-//        of a unit (32 channels x 128 pixels) into a staging ring with 1-D TMA bulk copies (cp.async.bulk +
-//        mbarrier complete_tx) -- up to 6 units (96 KB) in flight per SM with no register or LSU cost -- and
+//   bulk (default whenever every source plane is 16-byte aligned): warps 25-26 stream the raw fp32 / bf16 channel rows
+//        of a unit (32 channels x 128 pixels) into a staging ring with 16-byte cp.async (LDGSTS) copies whose
+//        completion is collected by an mbarrier -- up to 6 units (96 KB) in flight per SM, no registers held -- and
 //        warps 8-23 only convert staging -> swizzled bf16 operand (shared -> shared).  Their fence.proxy.async
-//        (MEMBAR.ALL.CTA) then has no global loads to wait for.
+//        (MEMBAR.ALL.CTA) then has no global loads to wait for.  (1-D TMA bulk copies were tried first: a 512-byte
+//        row per UBLKCP is too small, 11 GB/s per SM.)
 //   simt (fallback for unaligned planes, e.g. 125 x 125 maps, and the 2x2 pooling gather): warps 8-23 load from
 //        global memory themselves (64-channel units).
 #pragma once
@@ -35,16 +36,19 @@ constexpr int TILE_M = 128;           // pixels per tile (TMEM lanes)
 constexpr int KBLK = 64;              // channels per ring slot
 constexpr int STAGE_BYTES = TILE_M * KBLK * 2;
 constexpr int NPROD = 512;            // producer threads
-constexpr int NEPI = 256;             // epilogue threads: warp w owns TMEM lanes 32*(w%4).. and column groups w/4, w/4+2, ..
-constexpr int NTHREADS = NEPI + NPROD + 64;
+constexpr int NEPI = 256;             // epilogue threads (simt mode): warp w owns TMEM lanes 32*(w%4).. and column groups w/4, w/4+2, ..
+constexpr int NEPI_BULK = 512;        // bulk mode: warps 8-15 join the epilogue (column groups w/4, w/4+4), warps 16-23 convert
+constexpr int NLOADW = 2;             // bulk mode: loader warps (cp.async row copies), alternating units
+constexpr int NTHREADS = NEPI + NPROD + 32 + 32 * NLOADW;
 constexpr int MMA_WARP = (NEPI + NPROD) / 32;
-constexpr int TMA_WARP = MMA_WARP + 1;      // bulk mode: issues the cp.async.bulk row copies
+constexpr int LOAD_WARP0 = MMA_WARP + 1;    // bulk mode: first loader warp
 constexpr int UNIT_K = 32;            // bulk mode: channels per unit
 constexpr int RAW_ROW = 512;          // bulk mode: staging bytes per channel row (128 fp32; bf16 rows use the first 256)
 constexpr int RAW_SLOT = UNIT_K * RAW_ROW;            // 16 KB
 constexpr int GRAW_SLOT = UNIT_K * 256;               // reset-gate pre-activations (bf16) of a unit
 constexpr int A_SLOT_BULK = TILE_M * UNIT_K * 2;      // 8 KB operand slot
 constexpr int MAX_RAW = 6, MAX_ASLOT = 4;
+constexpr int EPI_STAGE = 2048;       // per epilogue warp: 32 channels x 32 pixels of bf16, transposes thread-per-pixel <-> 16-byte rows
 constexpr int MAXG = 8;               // NOUT <= 256 -> at most 8 groups of 32 output channels
 constexpr int MAXKB = 5;              // K <= 320 channels per contraction
 constexpr size_t SMEM_CAP = 229376;   // dynamic shared memory budget (227 KB opt-in limit minus static use)
@@ -58,24 +62,30 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait returns after a short hardware time-out, so a bare loop polls every ~40 cycles: with 16 converter warps
+// waiting for data that was 53 % of all issued instructions (ncu source view) and starved the epilogue warps.
+// Waits that have slack therefore back off with nanosleep after a failed poll.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
-    do {
+    for (;;) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
+        if (done) break;
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    }
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); bytes past `src_bytes` (0..16) are zero-filled and
+// not read.  Completion is collected per thread by cp_async_arrive.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
 }
-// 1-D TMA bulk copy global -> shared; completion is signalled on `bar` as `bytes` of transaction count.
-// dst, src and bytes must be multiples of 16.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+// the mbarrier receives one (pre-counted) arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -216,6 +226,8 @@ struct GemmParams {
     int nstage;                              // simt mode: K-block ring depth (64-channel slots)
     int bulk, nraw, na;                      // bulk mode: on/off, staging ring depth, operand ring depth (32-channel slots)
     int reverse;                             // walk the tiles from the last to the first (L2 reuse between sweeps)
+    int out_vec;                             // bf16 output (and addend) planes are padded to whole tiles and 16-byte aligned:
+                                             // the epilogue moves them as 16-byte row pieces through a per-warp staging tile
     int tmem_cols;                           // power of two >= 2 * NOUT
     volatile unsigned* dbg;                  // optional host-mapped progress / trace words (bring-up only)
 };
@@ -261,7 +273,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const uint32_t w_off = 0;
     const uint32_t a_off = w_off + (uint32_t)nkb * wblk_bytes;
     const uint32_t raw_off = a_off + (uint32_t)(bulk ? P.na * A_SLOT_BULK : P.nstage * STAGE_BYTES);
-    const uint32_t bias_off = raw_off + (bulk ? (uint32_t)P.nraw * raw_slot_bytes : 0u);
+    const uint32_t stg_off = raw_off + (bulk ? (uint32_t)P.nraw * raw_slot_bytes : 0u);
+    const uint32_t bias_off = stg_off + (uint32_t)((bulk ? NEPI_BULK : NEPI) / 32) * EPI_STAGE;
     const uint32_t bar_off = bias_off + 1024;
     const uint32_t tab_off = bar_off + 512;                  // per-channel source table: MAXKB*64 entries of 32 bytes
     // barriers: full[8], empty[8], tmem_full[2], tmem_empty[2], (tmem slot), raw_full[8], raw_empty[8]
@@ -278,9 +291,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
     if (tid == 0) {
-        for (int s = 0; s < nslot; ++s) { mbar_init(full0 + 8 * s, NPROD / 2); mbar_init(empty0 + 8 * s, 1); }
-        if (bulk) for (int s = 0; s < P.nraw; ++s) { mbar_init(rfull0 + 8 * s, 1); mbar_init(rempty0 + 8 * s, NPROD / 2); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NEPI); }
+        // one producer / converter group arrives per operand slot: 256 threads (simt) or 128 threads (bulk)
+        for (int s = 0; s < nslot; ++s) { mbar_init(full0 + 8 * s, bulk ? 128 : NPROD / 2); mbar_init(empty0 + 8 * s, 1); }
+        if (bulk) for (int s = 0; s < P.nraw; ++s) { mbar_init(rfull0 + 8 * s, 32); mbar_init(rempty0 + 8 * s, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, bulk ? NEPI_BULK : NEPI); }
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
@@ -290,18 +304,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = (i < P.nbias) ? __ldg(P.bias + i) : 0.f;
     }
     {
-        const int chunks_per_row = nkb * 8;                 // 16-byte chunks (8 bf16) per weight row
-        for (int idx = tid; idx < NOUT * chunks_per_row; idx += NTHREADS) {
+        // 16-byte chunks (8 bf16) of the swizzled image; two chunks per thread and iteration so that four 16-byte loads
+        // are in flight (the prologue is latency-bound: weights come from L2)
+        const int chunks_per_row = nkb * 8, total = NOUT * chunks_per_row;
+        auto wload = [&](int idx, float (&v)[8]) {
             const int n = idx / chunks_per_row, ch = idx % chunks_per_row;
-            const int kb = ch >> 3, j = ch & 7, k0 = kb * KBLK + j * 8;
+            const int k0 = (ch >> 3) * KBLK + (ch & 7) * 8;
             const bool second = n >= P.nrow1;
             const float* wrow = second ? (P.W2 + (long)(n - P.nrow1) * P.w2_ld) : (P.W + (long)n * P.w_ld);
             const int klim = second ? (P.k2 < K ? P.k2 : K) : K;
-            float v[8];
+            const long ks = second ? 1 : P.w_ks;
+            if (n < P.nout_store && ks == 1 && k0 + 8 <= klim && (reinterpret_cast<uintptr_t>(wrow + k0) & 15) == 0) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(wrow + k0)), b = __ldg(reinterpret_cast<const float4*>(wrow + k0) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim && n < P.nout_store) ? __ldg(wrow + (long)(k0 + u) * (second ? 1 : P.w_ks)) : 0.f;
-            uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim && n < P.nout_store) ? __ldg(wrow + (long)(k0 + u) * ks) : 0.f;
+            }
+        };
+        auto wstore = [&](int idx, const float (&v)[8]) {
+            const int n = idx / chunks_per_row, ch = idx % chunks_per_row;
+            const int kb = ch >> 3, j = ch & 7;
+            const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             *reinterpret_cast<uint4*>(sm + w_off + kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
+        };
+        for (int idx = tid; idx < total; idx += 2 * NTHREADS) {
+            float v0[8], v1[8];
+            const int idx1 = idx + NTHREADS;
+            wload(idx, v0);
+            if (idx1 < total) wload(idx1, v1);
+            wstore(idx, v0);
+            if (idx1 < total) wstore(idx1, v1);
         }
     }
     // where every reduction channel lives: plane base pointer, dtype, optional reset-gate map and folded GN affine
@@ -342,19 +375,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const int ntiles = (N + TILE_M - 1) / TILE_M;
     const int acc_stride = P.tmem_cols >> 1;                // columns per accumulator stage
 
-    if (warp >= NEPI / 32 && warp < MMA_WARP) {
+    const int nepw = bulk ? NEPI_BULK / 32 : NEPI / 32;       // epilogue warps
+    if (warp >= nepw && warp < MMA_WARP) {
         // =========================================================================== producers
         // Shared layout of a ring slot (canonical UMMA MN-major, SWIZZLE_128B): 1024-byte atoms of 8 channels x 64
         // pixels; atom(mblk, kblk) at mblk*8192 + kblk*1024; inside: channel (k&7)*128 B, 16-byte chunk
         // j = (pixel%64)/8 stored at chunk position j ^ (k&7).  Units (tile, K block) are streamed two deep.
-        const int pt = tid - NEPI;
+        // simt: warps 8-23, two groups of 256 threads; bulk: warps 16-23, two converter groups of 128 threads
+        const int pt = bulk ? tid - NEPI_BULK : tid - NEPI;
         const Segs& S = P.seg;
         // Two independent producer groups of 256 threads; group g fills the units (tile, K block) with index u = g (mod 2).
         // A thread holds NO loads in flight when it publishes its unit: fence.proxy.async compiles to MEMBAR.ALL.CTA,
         // which waits for every outstanding load of the thread, so a per-thread software prefetch would be serialised
         // by the fence.  Memory-level parallelism comes from the two groups (and the 8-deep ring) instead.
-        const int grp = pt >> 8, tl = pt & 255;
-        const int ch0 = tl >> 4, px8 = tl & 15;               // chunk c handles channel-in-block ch0 + 16c, pixels px8*8..+7
+        const int grp = bulk ? pt >> 7 : pt >> 8, tl = bulk ? pt & 127 : pt & 255;
+        const int ch0 = tl >> 4, px8 = tl & 15;               // simt: chunk c handles channel-in-block ch0 + 16c, pixels px8*8..+7
         constexpr int NCH = 4;
         int trace_i = 0;
         bool aligned = (N & 3) == 0;
@@ -484,16 +519,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 const uint32_t phase = (uint32_t)((u / P.nstage) & 1);
                 if (EPI != EPI_POOL && aligned && (tile + 1) * TILE_M <= N) issue_fast((int)tile, kb, b);
                 else issue_slow((int)tile, kb, b);
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                mbar_wait<64>(empty0 + 8 * stage, phase ^ 1);
                 commit(kb, stage, b);
             }
         } else {
-            // ---- bulk mode: staging (raw rows landed by TMA) -> bf16 swizzled operand slot.  Unit = 32 channels x 128
-            // pixels; a thread converts 8 pixels of channels ch0 and ch0 + 16.  Operand slot: 1024-byte atoms of 8 channels x
-            // 64 pixels, atom(mblk, kblk) at mblk*4096 + kblk*1024.
-            const uint32_t so[2] = {
-                (uint32_t)((px8 >> 3) * 4096 + (ch0 >> 3) * 1024 + (ch0 & 7) * 128 + (((px8 & 7) ^ (ch0 & 7)) << 4)),
-                (uint32_t)((px8 >> 3) * 4096 + ((ch0 + 16) >> 3) * 1024 + (ch0 & 7) * 128 + (((px8 & 7) ^ (ch0 & 7)) << 4))};
+            // ---- bulk mode: staging (raw rows landed by cp.async) -> bf16 swizzled operand slot.  Unit = 32 channels x 128
+            // pixels; a thread (ch0 = 0..7) converts 8 pixels of channels ch0 + 8c, c = 0..3.  Operand slot: 1024-byte
+            // atoms of 8 channels x 64 pixels, atom(mblk, kblk) at mblk*4096 + kblk*1024 -> chunk c is K-atom c.
+            const uint32_t so0 = (uint32_t)((px8 >> 3) * 4096 + ch0 * 128 + (((px8 & 7) ^ ch0) << 4));
             // fp32 rows: a thread's 32 bytes are fetched as two 16-byte pieces; odd groups of four threads fetch the
             // upper piece first so that a quarter-warp touches all 32 banks (conflict-free LDS.128)
             const bool swp = ((px8 >> 2) & 1) != 0;
@@ -508,11 +541,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 const long pbase = tile * TILE_M + px_off;
                 const int nv = (pbase >= N) ? 0 : ((N - pbase >= 8) ? 8 : (int)(N - pbase));   // valid pixels of my 8
                 const uint8_t* rawp = sm + raw_off + rs * raw_slot_bytes;
-                mbar_wait(rfull0 + 8 * rs, rph);
-                uint4 pk[2];
+                mbar_wait<96>(rfull0 + 8 * rs, rph);
+                uint4 pk[4];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int ch = ch0 + 16 * c;
+                for (int c = 0; c < 4; ++c) {
+                    const int ch = ch0 + 8 * c;
                     const ChanEnt* e = ctab + kb * UNIT_K + ch;
                     const int meta = e->meta;
                     float v[8];
@@ -548,21 +581,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                     }
                 }
                 mbar_arrive(rempty0 + 8 * rs);               // staging slot consumed (values are in registers)
-                mbar_wait(empty0 + 8 * as, aph ^ 1);
+                mbar_wait<64>(empty0 + 8 * as, aph ^ 1);
                 uint8_t* st = sm + a_off + as * A_SLOT_BULK;
-                *reinterpret_cast<uint4*>(st + so[0]) = pk[0];
-                *reinterpret_cast<uint4*>(st + so[1]) = pk[1];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(st + so0 + c * 1024) = pk[c];
                 fence_proxy_async();                         // generic-proxy stores -> visible to tcgen05.mma
                 mbar_arrive(full0 + 8 * as);
-                if (warp == NEPI / 32 && kb == nu - 1) { TC_TRACE(1, trace_i); ++trace_i; }
+                if (warp == NEPI_BULK / 32 && kb == nu - 1) { TC_TRACE(1, trace_i); ++trace_i; }
             }
         }
-    } else if (warp == TMA_WARP) {
-        // =========================================================================== bulk-copy issuer (bulk mode)
-        // lane c streams channel c of every unit: one 512-byte (fp32) or 256-byte (bf16) row, plus the 256-byte row of
-        // reset-gate pre-activations for gated channels.
+    } else if (warp >= LOAD_WARP0) {
+        // =========================================================================== loaders (bulk mode)
+        // Loader warp l streams the units u = l (mod NLOADW): per channel row one warp-wide 16-byte cp.async (512 B of an
+        // fp32 row; a bf16 row, 256 B, uses lanes 0-15), plus the row of reset-gate pre-activations for gated channels.
+        // Nothing is waited for here: the copies of up to `nraw` units stay in flight and each thread's completion is
+        // collected by the unit's mbarrier (cp.async.mbarrier.arrive.noinc).
         if (bulk) {
-            for (long u = 0;; ++u) {
+            for (long u = warp - LOAD_WARP0;; u += NLOADW) {
                 const long ti = u / nu;
                 const int kb = (int)(u - ti * nu);
                 long tile = blockIdx.x + ti * gridDim.x;
@@ -570,21 +605,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 if (P.reverse) tile = ntiles - 1 - tile;
                 const int rs = (int)(u % P.nraw);
                 const uint32_t rph = (uint32_t)((u / P.nraw) & 1);
-                const ChanEnt e = ctab[kb * UNIT_K + lane];
                 const long p0 = tile * TILE_M;
                 const int nvalid = (N - p0 >= TILE_M) ? TILE_M : (int)(N - p0);
-                // bf16 maps are internal and padded to whole tiles: always a full row.  fp32 maps: only the valid part
-                // (N % 4 == 0 is a precondition of bulk mode, so the size stays a multiple of 16).
-                uint32_t bytes = 0, gbytes = 0;
-                if (e.meta & 1) { bytes = (e.meta & 2) ? 256u : (uint32_t)nvalid * 4u; if (GATED && (e.meta & 4)) gbytes = 256u; }
-                const uint32_t total = __reduce_add_sync(0xffffffffu, bytes + gbytes);
-                mbar_wait(rempty0 + 8 * rs, rph ^ 1);
-                const uint32_t bar = rfull0 + 8 * rs;
-                if (lane == 0) mbar_arrive_expect_tx(bar, total);
-                __syncwarp();
+                // valid bytes of my 16-byte chunk in an fp32 row (tail tile: the rest is zero-filled)
+                const int vb = nvalid * 4 - lane * 16;
+                const uint32_t fbytes = vb >= 16 ? 16u : (vb > 0 ? (uint32_t)vb : 0u);
                 const uint32_t dst = base + raw_off + rs * raw_slot_bytes;
-                if (bytes) bulk_g2s(dst + lane * RAW_ROW, e.ptr + p0 * ((e.meta & 2) ? 2 : 4), bytes, bar);
-                if (gbytes) bulk_g2s(dst + RAW_SLOT + lane * 256, e.gptr + p0 * 2, gbytes, bar);
+                mbar_wait<96>(rempty0 + 8 * rs, rph ^ 1);
+                // rows are addressed arithmetically from the segment description (kernel parameters, uniform registers):
+                // a table lookup per row would put two dependent shared-memory round trips in front of every copy
+                const Segs& S = P.seg;
+                const int k_lo = kb * UNIT_K, k_hi = (k_lo + UNIT_K < K) ? k_lo + UNIT_K : K;
+                int cs = 0;
+#pragma unroll
+                for (int sg = 0; sg < 3; ++sg) {
+                    const int ce = S.cend[sg];
+                    const int lo = cs > k_lo ? cs : k_lo, hi = ce < k_hi ? ce : k_hi;
+                    if (lo < hi) {
+                        const bool b16 = S.kind[sg] != 0;
+                        const long rowb = S.plane[sg] * (b16 ? 2 : 4);
+                        const char* src = reinterpret_cast<const char*>(S.src[sg]) + (long)(lo - cs) * rowb + p0 * (b16 ? 2 : 4) + lane * 16;
+                        uint32_t d = dst + (uint32_t)(lo - k_lo) * RAW_ROW + lane * 16;
+                        const uint32_t nb = b16 ? 16u : fbytes;          // bf16 rows live in padded planes: always whole
+                        if (!b16 || lane < 16) {
+#pragma unroll 4
+                            for (int c = lo; c < hi; ++c) { cp_async16(d, src, nb); src += rowb; d += RAW_ROW; }
+                        }
+                        if (GATED && sg == S.gate_seg && lane < 16) {
+                            const long growb = S.gate_plane * 2;
+                            const char* g = reinterpret_cast<const char*>(S.gate_pre) + (long)(S.gate_ch0 + lo - cs) * growb + p0 * 2 + lane * 16;
+                            uint32_t gd = dst + RAW_SLOT + (uint32_t)(lo - k_lo) * 256 + lane * 16;
+#pragma unroll 4
+                            for (int c = lo; c < hi; ++c) { cp_async16(gd, g, 16u); g += growb; gd += 256; }
+                        }
+                    }
+                    cs = ce;
+                }
+                cp_async_arrive(rfull0 + 8 * rs);
             }
         }
     } else if (warp == MMA_WARP) {
@@ -593,12 +650,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         const uint32_t idesc = instr_desc_bf16(NOUT);
         int stage = 0; uint32_t phase = 0; int as = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            mbar_wait(tempty0 + 8 * as, aphase ^ 1);         // epilogue has drained this accumulator
+            mbar_wait<32>(tempty0 + 8 * as, aphase ^ 1);     // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * acc_stride);
             const int nunits = bulk ? nu : nkb;
             for (int kb = 0; kb < nunits; ++kb) {
-                mbar_wait(full0 + 8 * stage, phase);
+                mbar_wait<20>(full0 + 8 * stage, phase);
                 tc_fence_after();
                 if (lane == 0) {
                     if (bulk) {
@@ -635,71 +692,113 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         for (int g = 0; g < MAXG / 2; ++g) { st_s[g] = 0.f; st_ss[g] = 0.f; }
         int as = 0; uint32_t aphase = 0;
         const int ng = NOUT >> 5;
-        const int lq = warp & 3, ghalf = warp >> 2;
+        const int lq = warp & 3, ghalf = warp >> 2, gstep = nepw >> 2;   // column groups ghalf, ghalf + gstep, ...
         const int row = lq * 32 + lane;
         for (int vt = blockIdx.x; vt < ntiles; vt += gridDim.x) {
             const int tile = P.reverse ? ntiles - 1 - vt : vt;
             const long p = (long)tile * TILE_M + row;
             const bool valid = p < N;
-            const float vmask = valid ? 1.f : 0.f;
             const long pc = valid ? p : 0;
-            // the addend map (r-independent candidate part) does not depend on this tile's MMA: fetch it first
-            float adv[1][EPI == EPI_GN ? 32 : 1];
+            // the addend map (r-independent candidate part) does not depend on this tile's MMA: fetch it first.
+            // out_vec: as four 16-byte row pieces per lane (row c = (lane>>2) + 8j of the group, pixels 8*(lane&3)..+7 of
+            // this warp's 32), transposed to thread-per-pixel through the warp's staging tile; else element by element.
+            uint4 adraw[EPI == EPI_GN ? 4 : 1];
+            const long vrow0 = (long)tile * TILE_M + lq * 32 + (lane & 3) * 8;     // first pixel of my 16-byte row piece
             if constexpr (EPI == EPI_GN) {
-                if (P.addend != nullptr) {
+                if (P.addend != nullptr && ghalf < ng) {
+                    if (P.out_vec) {
 #pragma unroll
-                    for (int gi = 0; gi < MAXG / 2; ++gi) {
-                        const int g = ghalf + 2 * gi;
-                        if (g < ng && gi < 1) {
-                            const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) adv[gi][i] = __bfloat162float(ad[(long)i * P.out_plane]);
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            adraw[j] = __ldg(reinterpret_cast<const uint4*>(P.addend + (long)(ghalf * 32 + (lane >> 2) + 8 * j) * P.out_plane + vrow0));
                     }
                 }
             }
-            mbar_wait(tfull0 + 8 * as, aphase);
+            mbar_wait<32>(tfull0 + 8 * as, aphase);
             tc_fence_after();
             if (warp == 0) TC_TRACE(3, (vt - (int)blockIdx.x) / (int)gridDim.x);
             const uint32_t t_addr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(as * acc_stride);
 #pragma unroll
             for (int gi = 0; gi < MAXG / 2; ++gi) {
-                const int g = ghalf + 2 * gi;
+                const int g = ghalf + gstep * gi;
                 if (g < ng) {
                     float v[32];
                     tmem_ld32(t_addr + g * 32, v);
                     if constexpr (EPI == EPI_GN) {
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                        __nv_bfloat16* o = P.out + (long)(g * 32) * P.out_plane + pc;
                         const float* bs = sbias + g * 32;
-                        if (P.addend != nullptr) {
-                            if (gi < 1) {
+                        if (P.out_vec) {
+                            uint8_t* stg = sm + stg_off + warp * EPI_STAGE;          // [32 channels][32 pixels] bf16, warp-private
+                            const uint32_t vo = (uint32_t)((lane >> 2) * 64 + (lane & 3) * 16);
+                            if (P.addend != nullptr) {
+                                if (gi > 0) {
 #pragma unroll
-                                for (int i = 0; i < 32; ++i) v[i] += adv[0][i];
-                            } else {
+                                    for (int j = 0; j < 4; ++j)
+                                        adraw[j] = __ldg(reinterpret_cast<const uint4*>(P.addend + (long)(g * 32 + (lane >> 2) + 8 * j) * P.out_plane + vrow0));
+                                }
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + vo + j * 512) = adraw[j];
+                                __syncwarp();
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    v[i] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + i * 64 + lane * 2));
+                                __syncwarp();
+                            }
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
+                                *reinterpret_cast<__nv_bfloat16*>(stg + i * 64 + lane * 2) = __float2bfloat16(y0);
+                                *reinterpret_cast<__nv_bfloat16*>(stg + (i + 1) * 64 + lane * 2) = __float2bfloat16(y1);
+                                s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+                            }
+                            __syncwarp();
+                            // planes are padded to whole tiles: pixels past the map are written too (never read as data)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(P.out + (long)(g * 32 + (lane >> 2) + 8 * j) * P.out_plane + vrow0) =
+                                    *reinterpret_cast<const uint4*>(stg + vo + j * 512);
+                            __syncwarp();
+                        } else {
+                            __nv_bfloat16* o = P.out + (long)(g * 32) * P.out_plane + pc;
+                            if (P.addend != nullptr) {
                                 const __nv_bfloat16* ad = P.addend + (long)(g * 32) * P.out_plane + pc;
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) v[i] += __bfloat162float(ad[(long)i * P.out_plane]);
                             }
-                        }
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
-                            if (valid) { o[0] = __float2bfloat16(y0); o[P.out_plane] = __float2bfloat16(y1); }
-                            o += 2 * P.out_plane;
-                            s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+                            for (int i = 0; i < 32; i += 2) {
+                                const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
+                                if (valid) { o[0] = __float2bfloat16(y0); o[P.out_plane] = __float2bfloat16(y1); }
+                                o += 2 * P.out_plane;
+                                s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+                            }
                         }
-                        st_s[gi] += (s0 + s1) * vmask; st_ss[gi] += (q0 + q1) * vmask;
+                        if (valid) { st_s[gi] += s0 + s1; st_ss[gi] += q0 + q1; }
                     } else if constexpr (EPI == EPI_LRELU) {
                         // y = LeakyReLU(acc + bias) -> NCHW (bf16 or fp32)
                         const float* bs = sbias + g * 32;
+                        if (P.out_vec && P.out_f32 == nullptr) {
+                            uint8_t* stg = sm + stg_off + warp * EPI_STAGE;
+                            const uint32_t vo = (uint32_t)((lane >> 2) * 64 + (lane & 3) * 16);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int n = g * 32 + i;
-                            const float y = lrelu(v[i] + bs[i], P.slope);
-                            if (valid && n < P.nout_store) {
-                                if (P.out_f32) P.out_f32[(long)n * P.out_plane + p] = y;
-                                else P.out[(long)n * P.out_plane + p] = __float2bfloat16(y);
+                            for (int i = 0; i < 32; ++i)
+                                *reinterpret_cast<__nv_bfloat16*>(stg + i * 64 + lane * 2) = __float2bfloat16(lrelu(v[i] + bs[i], P.slope));
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int n = g * 32 + (lane >> 2) + 8 * j;
+                                if (n < P.nout_store)
+                                    *reinterpret_cast<uint4*>(P.out + (long)n * P.out_plane + vrow0) = *reinterpret_cast<const uint4*>(stg + vo + j * 512);
+                            }
+                            __syncwarp();
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int n = g * 32 + i;
+                                const float y = lrelu(v[i] + bs[i], P.slope);
+                                if (valid && n < P.nout_store) {
+                                    if (P.out_f32) P.out_f32[(long)n * P.out_plane + p] = y;
+                                    else P.out[(long)n * P.out_plane + p] = __float2bfloat16(y);
+                                }
                             }
                         }
                     } else if constexpr (EPI == EPI_POOL) {
@@ -743,7 +842,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         // per-CTA GroupNorm partials (fixed order: lanes -> lane quarters -> CTA)
 #pragma unroll
         for (int gi = 0; gi < MAXG / 2; ++gi) {
-            const int g = ghalf + 2 * gi;
+            const int g = ghalf + gstep * gi;
             if (g < ng) {
                 float a = warp_sum(st_s[gi]), b = warp_sum(st_ss[gi]);
                 if (lane == 0) { red[0][lq][g] = a; red[1][lq][g] = b; }
@@ -764,13 +863,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
 }
 
 // dynamic shared memory needed for a given problem; 0 if it cannot fit
-static inline size_t gemm_smem_fixed(int NOUT, int K) {
+static inline size_t gemm_smem_fixed(int NOUT, int K, bool bulk) {
     const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
-    return 1024 /*align slack*/ + (size_t)nkb * NOUT * 128 + 1024 /*bias*/ + 512 /*barriers*/ + (size_t)nkb * KBLK * 32 /*source table*/;
+    return 1024 /*align slack*/ + (size_t)nkb * NOUT * 128 + (size_t)((bulk ? NEPI_BULK : NEPI) / 32) * EPI_STAGE + 1024 /*bias*/ +
+           512 /*barriers*/ + (size_t)nkb * KBLK * 32 /*source table*/;
 }
 static inline size_t gemm_smem_bytes(int NOUT, int K, int* nstage_out) {
     const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
-    const size_t fixed = gemm_smem_fixed(NOUT, K);
+    const size_t fixed = gemm_smem_fixed(NOUT, K, false);
     const size_t cap = SMEM_CAP;
     if (fixed + 2 * STAGE_BYTES > cap || nkb > MAXKB) return 0;
     int ns = (int)((cap - fixed) / STAGE_BYTES);
@@ -781,13 +881,18 @@ static inline size_t gemm_smem_bytes(int NOUT, int K, int* nstage_out) {
 // bulk mode: operand ring (na slots of 8 KB) + staging ring (nraw slots of 16 KB, +8 KB each when gated); 0 if it cannot fit
 static inline size_t gemm_smem_bytes_bulk(int NOUT, int K, bool gated, int* nraw_out, int* na_out) {
     const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
-    const size_t fixed = gemm_smem_fixed(NOUT, K);
+    const size_t fixed = gemm_smem_fixed(NOUT, K, true);
     if (nkb > MAXKB || fixed >= SMEM_CAP) return 0;
     const size_t avail = SMEM_CAP - fixed, slot = (size_t)RAW_SLOT + (gated ? GRAW_SLOT : 0);
     for (int na = 3; na >= 2; --na) {
         if (avail < (size_t)na * A_SLOT_BULK + 2 * slot) continue;
         int nraw = (int)((avail - (size_t)na * A_SLOT_BULK) / slot);
         if (nraw > MAX_RAW) nraw = MAX_RAW;
+        // The staging depth must be a multiple of the number of loader warps / converter groups (2): unit u and unit
+        // u + nraw then belong to the same loader and the same group, so every slot has ONE producer and ONE consumer
+        // and a parity wait can never be two phases behind.  With an odd depth a loader can run ahead of the other
+        // group's consumption and pass a wait on the aliased parity (found as a hang; tools/sim_pipeline.py).
+        nraw &= ~1;
         if (na == 3 && nraw == MAX_RAW && avail >= (size_t)MAX_ASLOT * A_SLOT_BULK + (size_t)MAX_RAW * slot) na = MAX_ASLOT;
         *nraw_out = nraw; *na_out = na;
         return fixed + (size_t)na * A_SLOT_BULK + (size_t)nraw * slot;
@@ -816,6 +921,8 @@ static inline size_t plan_launch(GemmParams& P, int epi, bool allow_bulk) {
     if (bulk) { smem = gemm_smem_bytes_bulk(P.NOUT, P.K, gated, &nraw, &na); if (smem == 0) bulk = false; }
     if (!bulk) smem = gemm_smem_bytes(P.NOUT, P.K, &nstage);
     P.nstage = nstage; P.bulk = bulk ? 1 : 0; P.nraw = nraw; P.na = na;
+    P.out_vec = (P.out != nullptr && P.out_plane >= npad && P.out_plane % 8 == 0 && (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 &&
+                 (P.addend == nullptr || (reinterpret_cast<uintptr_t>(P.addend) & 15) == 0) && (epi == EPI_GN || epi == EPI_LRELU)) ? 1 : 0;
     int cols = 32;
     while (cols < 2 * P.NOUT) cols <<= 1;
     P.tmem_cols = cols;

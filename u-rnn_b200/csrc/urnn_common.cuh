@@ -50,6 +50,8 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 // ex2.approx / rcp.approx have a relative error of ~2 ulp: |err| of silu/sigmoid stays below 1e-6 on O(1) values,
 // inside the fp32 parity tolerance (atol 1e-5)
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// tanh(x) = 1 - 2/(1 + e^{2x}) with ex2.approx / rcp.approx: absolute error ~1e-6, saturates correctly at +-1
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 __device__ __forceinline__ float lrelu(float x, float slope) { return x >= 0.f ? x : x * slope; }
 __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
 
