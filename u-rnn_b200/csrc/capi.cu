@@ -236,6 +236,8 @@ static int ed_step_impl(const urnn_ed_desc* d, const urnn_ed_params* p, const St
         long np[3];
         for (int k = 0; k < 3; ++k) np[k] = tc_pad_plane((long)pl.h[k] * pl.w[k]);
         tc_reset_direction();
+        URNN_TRY(tc_counters_begin(&pl.enc[0], pl.cell_ws, pl.cell_ws_bytes, st));
+        struct CountersGuard { ~CountersGuard() { tc_counters_end(); } } counters_guard;
         for (int k = 0; k < 3; ++k) {
             int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
             URNN_TRY(conv1x1_lrelu_fwd_tc(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, 0,

@@ -19,6 +19,10 @@ static int g_num_sms = 0;
 // predecessor touched last (still in the 126 MB L2).  Entry points reset it, so a given call sequence is reproducible.
 static thread_local int g_dir = 0;
 void tc_reset_direction() { g_dir = 0; }
+static thread_local bool g_counters_clean = false;
+// step driver: clear the cell workspace's ticket counters now and skip the per-cell memset until tc_counters_end()
+int tc_counters_begin(const urnn_cell_desc* d, void* cell_ws, size_t ws_bytes, cudaStream_t st);
+void tc_counters_end() { g_counters_clean = false; }
 static inline long pad_plane(long n) { return (n + tc::TILE_M - 1) / tc::TILE_M * tc::TILE_M; }
 long tc_pad_plane(long n) { return pad_plane(n); }
 
@@ -116,55 +120,41 @@ int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const v
     return URNN_OK;
 }
 
-// h' = (1-z)*h + z*tanh(GN2(C)),  z = sigmoid(GN1(G)[:F]); G and C are bf16 maps with padded planes.
-// Pixel-major like the GEMM sweeps: blockIdx.y = block of 256*VEC pixels, blockIdx.x = group of BLEND_CH channels.
-constexpr int BLEND_CH = 8;
+// h' = (1-z)*h + z*tanh(GN2(C)),  z = sigmoid(GN1(G)[:F]); G and C are bf16 maps with padded planes (gplane).
+// Channel-major streaming: thread = VEC consecutive pixels of one channel, four sequential streams per channel.
 template <int VEC>
 __global__ void __launch_bounds__(256)
 cgru_blend_bf16_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16* __restrict__ C,
                        const float* __restrict__ h, const float* __restrict__ sc1, const float* __restrict__ sh1,
                        const float* __restrict__ sc2, const float* __restrict__ sh2, float* __restrict__ h_out,
-                       long N, long gplane, int F, int reverse) {
+                       long N, long gplane, unsigned nq, long total) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const long pb = reverse ? (long)(gridDim.y - 1 - blockIdx.y) : (long)blockIdx.y;
-    const long p = (pb * 256 + threadIdx.x) * VEC;
-    if (p >= N) return;
-    const int c0 = blockIdx.x * BLEND_CH;
-    float gv[BLEND_CH][VEC], cv[BLEND_CH][VEC], hv[BLEND_CH][VEC];
-#pragma unroll
-    for (int j = 0; j < BLEND_CH; ++j) {
-        const int c = c0 + j;
-        if (c < F) {
-            if constexpr (VEC == 4) {
-                const uint2 gw = __ldg(reinterpret_cast<const uint2*>(G + (long)c * gplane + p));
-                const uint2 cw = __ldg(reinterpret_cast<const uint2*>(C + (long)c * gplane + p));
-                const float4 hh = __ldg(reinterpret_cast<const float4*>(h + (long)c * N + p));
-                tc::unpack_bf16x2(gw.x, gv[j][0], gv[j][1]); tc::unpack_bf16x2(gw.y, gv[j][2], gv[j][3]);
-                tc::unpack_bf16x2(cw.x, cv[j][0], cv[j][1]); tc::unpack_bf16x2(cw.y, cv[j][2], cv[j][3]);
-                hv[j][0] = hh.x; hv[j][1] = hh.y; hv[j][2] = hh.z; hv[j][3] = hh.w;
-            } else {
-                gv[j][0] = __bfloat162float(G[(long)c * gplane + p]);
-                cv[j][0] = __bfloat162float(C[(long)c * gplane + p]);
-                hv[j][0] = __ldg(h + (long)c * N + p);
-            }
-        }
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const unsigned c = (unsigned)(idx / nq);
+    const long p = (idx - (long)c * nq) * VEC;
+    float gv[VEC], cv[VEC], hv[VEC], o[VEC];
+    if constexpr (VEC == 4) {
+        const uint2 gw = __ldg(reinterpret_cast<const uint2*>(G + (long)c * gplane + p));
+        const uint2 cw = __ldg(reinterpret_cast<const uint2*>(C + (long)c * gplane + p));
+        const float4 hh = __ldg(reinterpret_cast<const float4*>(h + (long)c * N + p));
+        tc::unpack_bf16x2(gw.x, gv[0], gv[1]); tc::unpack_bf16x2(gw.y, gv[2], gv[3]);
+        tc::unpack_bf16x2(cw.x, cv[0], cv[1]); tc::unpack_bf16x2(cw.y, cv[2], cv[3]);
+        hv[0] = hh.x; hv[1] = hh.y; hv[2] = hh.z; hv[3] = hh.w;
+    } else {
+        gv[0] = __bfloat162float(G[(long)c * gplane + p]);
+        cv[0] = __bfloat162float(C[(long)c * gplane + p]);
+        hv[0] = __ldg(h + (long)c * N + p);
     }
+    const float a1 = __ldg(sc1 + c), b1 = __ldg(sh1 + c), a2 = __ldg(sc2 + c), b2 = __ldg(sh2 + c);
 #pragma unroll
-    for (int j = 0; j < BLEND_CH; ++j) {
-        const int c = c0 + j;
-        if (c < F) {
-            const float a1 = __ldg(sc1 + c), b1 = __ldg(sh1 + c), a2 = __ldg(sc2 + c), b2 = __ldg(sh2 + c);
-            float o[VEC];
-#pragma unroll
-            for (int u = 0; u < VEC; ++u) {
-                const float z = sigmoid_fast(fmaf(gv[j][u], a1, b1)), t = tanh_fast(fmaf(cv[j][u], a2, b2));
-                o[u] = (1.f - z) * hv[j][u] + z * t;
-            }
-            if constexpr (VEC == 4) *reinterpret_cast<float4*>(h_out + (long)c * N + p) = make_float4(o[0], o[1], o[2], o[3]);
-            else h_out[(long)c * N + p] = o[0];
-        }
+    for (int u = 0; u < VEC; ++u) {
+        const float z = sigmoid_fast(fmaf(gv[u], a1, b1)), t = tanh_fast(fmaf(cv[u], a2, b2));
+        o[u] = (1.f - z) * hv[u] + z * t;
     }
+    if constexpr (VEC == 4) *reinterpret_cast<float4*>(h_out + (long)c * N + p) = make_float4(o[0], o[1], o[2], o[3]);
+    else h_out[(long)c * N + p] = o[0];
 }
 
 struct CellWsBf16 {
@@ -193,6 +183,14 @@ static size_t cell_ws_bf16(const urnn_cell_desc* d, void* ws, size_t ws_bytes, C
 
 size_t cgru_fwd_bf16_workspace(const urnn_cell_desc* d) { return cell_ws_bf16(d, nullptr, 0, nullptr); }
 
+int tc_counters_begin(const urnn_cell_desc* d, void* cell_ws, size_t ws_bytes, cudaStream_t st) {
+    CellWsBf16 w;
+    cell_ws_bf16(d, cell_ws, ws_bytes, &w);          // the counters sit at the same offset for every cell geometry
+    URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
+    g_counters_clean = true;
+    return URNN_OK;
+}
+
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st, long x_plane) {
     if (d->ksize != 1) {                                                                 // k>1: fp32 taps path
@@ -213,7 +211,8 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     CellWsBf16 w;
     size_t need = cell_ws_bf16(d, ws, ws_bytes, &w);
     if (need > ws_bytes) { set_error("cgru_fwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
-    URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
+    // the ticket counters reset themselves (last CTA); the step driver clears them once per step instead of once per cell
+    if (!g_counters_clean) URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
 
     tc::GemmParams P; tc_params_defaults(P);
     // segments [x | e | h]; missing ones get zero width
@@ -262,24 +261,23 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     {
         static const bool pdl = !(getenv("URNN_PDL") && getenv("URNN_PDL")[0] == '0');
         const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0;
-        const long per = vec ? 1024 : 256;
+        const long nq = vec ? N / 4 : N, total = nq * F;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((F + BLEND_CH - 1) / BLEND_CH), (unsigned)((N + per - 1) / per));
+        cfg.gridDim = dim3((unsigned)((total + 255) / 256));
         cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-        URNN_CHECK_ARG(cfg.gridDim.y <= 65535u, "cgru_fwd(bf16): grid of %ld cells too large for the blend sweep", N);
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-        const int rev = g_dir; g_dir ^= 1;
+        g_dir ^= 1;
         if (vec)
             URNN_CUDA(cudaLaunchKernelEx(&cfg, cgru_blend_bf16_kernel<4>, (const __nv_bfloat16*)w.GP, (const __nv_bfloat16*)w.C, h,
                                          (const float*)w.scale1, (const float*)w.shift1, (const float*)w.scale2,
-                                         (const float*)w.shift2, h_out, N, Np, F, rev));
+                                         (const float*)w.shift2, h_out, N, Np, (unsigned)nq, total));
         else
             URNN_CUDA(cudaLaunchKernelEx(&cfg, cgru_blend_bf16_kernel<1>, (const __nv_bfloat16*)w.GP, (const __nv_bfloat16*)w.C, h,
                                          (const float*)w.scale1, (const float*)w.shift1, (const float*)w.scale2,
-                                         (const float*)w.shift2, h_out, N, Np, F, rev));
+                                         (const float*)w.shift2, h_out, N, Np, (unsigned)nq, total));
     }
     URNN_LAUNCH_CHECK();
     return URNN_OK;

@@ -48,7 +48,7 @@ constexpr int RAW_SLOT = UNIT_K * RAW_ROW;            // 16 KB
 constexpr int GRAW_SLOT = UNIT_K * 256;               // reset-gate pre-activations (bf16) of a unit
 constexpr int A_SLOT_BULK = TILE_M * UNIT_K * 2;      // 8 KB operand slot
 constexpr int MAX_RAW = 6, MAX_ASLOT = 4;
-constexpr int EPI_STAGE = 2048;       // per epilogue warp: 32 channels x 32 pixels of bf16, transposes thread-per-pixel <-> 16-byte rows
+constexpr int EPI_STAGE = 1024;       // per epilogue warp: 16 channels x 32 pixels of bf16, transposes thread-per-pixel <-> 16-byte rows
 constexpr int MAXG = 8;               // NOUT <= 256 -> at most 8 groups of 32 output channels
 constexpr int MAXKB = 5;              // K <= 320 channels per contraction
 constexpr size_t SMEM_CAP = 229376;   // dynamic shared memory budget (227 KB opt-in limit minus static use)
@@ -82,6 +82,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // not read.  Completion is collected per thread by cp_async_arrive.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+// 8-byte variant (L1-allocating; .cg only exists for 16 bytes): the 2x2 pooling gather moves (dx0, dx1) pairs
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
 }
 // the mbarrier receives one (pre-counted) arrival from this thread once all its earlier cp.async have landed
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
@@ -328,13 +332,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             *reinterpret_cast<uint4*>(sm + w_off + kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
         };
-        for (int idx = tid; idx < total; idx += 2 * NTHREADS) {
-            float v0[8], v1[8];
-            const int idx1 = idx + NTHREADS;
-            wload(idx, v0);
-            if (idx1 < total) wload(idx1, v1);
-            wstore(idx, v0);
-            if (idx1 < total) wstore(idx1, v1);
+        // every CTA reads the same weights at the same time: start each CTA at a different 512-byte block so that the
+        // L2 slices are not all asked for the same lines at once
+        const int nrot = total >> 5, rot = (int)((blockIdx.x * 37u) % (unsigned)nrot) << 5;
+        for (int it = tid; it < total; it += 4 * NTHREADS) {
+            float v[4][8]; int id[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int lin = it + q * NTHREADS;
+                id[q] = lin < total ? (lin + rot >= total ? lin + rot - total : lin + rot) : -1;
+                if (id[q] >= 0) wload(id[q], v[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (id[q] >= 0) wstore(id[q], v[q]);
         }
     }
     // where every reduction channel lives: plane base pointer, dtype, optional reset-gate map and folded GN affine
@@ -616,6 +627,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 // a table lookup per row would put two dependent shared-memory round trips in front of every copy
                 const Segs& S = P.seg;
                 const int k_lo = kb * UNIT_K, k_hi = (k_lo + UNIT_K < K) ? k_lo + UNIT_K : K;
+                if constexpr (EPI == EPI_POOL) {
+                    // tile slot = 4*quad + 2*dy + dx: lane q gathers quad tile*32 + q of every channel with two 8-byte
+                    // copies (the dx pair of the upper and of the lower image row); single fp32 source map
+                    const long Q = tile * 32 + lane, nquads = (long)N >> 2;
+                    const int w2 = P.img_w >> 1;
+                    const long qy = Q / w2, qx = Q - qy * w2;
+                    const uint32_t nb = Q < nquads ? 8u : 0u;
+                    const long rowb = S.plane[0] * 4;
+                    const char* src = reinterpret_cast<const char*>(S.src[0]) + (long)k_lo * rowb + (nb ? ((2 * qy) * (long)P.img_w + 2 * qx) * 4 : 0);
+                    const long down = (long)P.img_w * 4;
+                    uint32_t d = dst + lane * 16;
+#pragma unroll 4
+                    for (int c = k_lo; c < k_hi; ++c) { cp_async8(d, src, nb); cp_async8(d + 8, src + down, nb); src += rowb; d += RAW_ROW; }
+                    cp_async_arrive(rfull0 + 8 * rs);
+                    continue;
+                }
                 int cs = 0;
 #pragma unroll
                 for (int sg = 0; sg < 3; ++sg) {
@@ -703,13 +730,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             // out_vec: as four 16-byte row pieces per lane (row c = (lane>>2) + 8j of the group, pixels 8*(lane&3)..+7 of
             // this warp's 32), transposed to thread-per-pixel through the warp's staging tile; else element by element.
             uint4 adraw[EPI == EPI_GN ? 4 : 1];
-            const long vrow0 = (long)tile * TILE_M + lq * 32 + (lane & 3) * 8;     // first pixel of my 16-byte row piece
+            // 16-byte row pieces: lane -> row (lane>>1) of a 16-channel half group, pixels 16*(lane&1).. of this warp's 32
+            const long vrow0 = (long)tile * TILE_M + lq * 32 + (lane & 1) * 16;
+            const int vrow = lane >> 1;
             if constexpr (EPI == EPI_GN) {
-                if (P.addend != nullptr && ghalf < ng) {
-                    if (P.out_vec) {
+                if (P.addend != nullptr && ghalf < ng && P.out_vec) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            adraw[j] = __ldg(reinterpret_cast<const uint4*>(P.addend + (long)(ghalf * 32 + (lane >> 2) + 8 * j) * P.out_plane + vrow0));
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const uint4* a = reinterpret_cast<const uint4*>(P.addend + (long)(ghalf * 32 + hh * 16 + vrow) * P.out_plane + vrow0);
+                        adraw[2 * hh] = __ldg(a); adraw[2 * hh + 1] = __ldg(a + 1);
                     }
                 }
             }
@@ -727,36 +756,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
                         const float* bs = sbias + g * 32;
                         if (P.out_vec) {
-                            uint8_t* stg = sm + stg_off + warp * EPI_STAGE;          // [32 channels][32 pixels] bf16, warp-private
-                            const uint32_t vo = (uint32_t)((lane >> 2) * 64 + (lane & 3) * 16);
-                            if (P.addend != nullptr) {
-                                if (gi > 0) {
+                            uint8_t* stg = sm + stg_off + warp * EPI_STAGE;          // [16 channels][32 pixels] bf16, warp-private
+                            const uint32_t vo = (uint32_t)(vrow * 64 + (lane & 1) * 32);
+                            if (P.addend != nullptr && gi > 0) {
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j)
-                                        adraw[j] = __ldg(reinterpret_cast<const uint4*>(P.addend + (long)(g * 32 + (lane >> 2) + 8 * j) * P.out_plane + vrow0));
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const uint4* a = reinterpret_cast<const uint4*>(P.addend + (long)(g * 32 + hh * 16 + vrow) * P.out_plane + vrow0);
+                                    adraw[2 * hh] = __ldg(a); adraw[2 * hh + 1] = __ldg(a + 1);
+                                }
+                            }
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                if (P.addend != nullptr) {
+                                    *reinterpret_cast<uint4*>(stg + vo) = adraw[2 * hh];
+                                    *reinterpret_cast<uint4*>(stg + vo + 16) = adraw[2 * hh + 1];
+                                    __syncwarp();
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j)
+                                        v[16 * hh + j] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + j * 64 + lane * 2));
+                                    __syncwarp();
                                 }
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + vo + j * 512) = adraw[j];
+                                for (int j = 0; j < 16; j += 2) {
+                                    const int i = 16 * hh + j;
+                                    const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
+                                    *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) = __float2bfloat16(y0);
+                                    *reinterpret_cast<__nv_bfloat16*>(stg + (j + 1) * 64 + lane * 2) = __float2bfloat16(y1);
+                                    s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
+                                }
                                 __syncwarp();
-#pragma unroll
-                                for (int i = 0; i < 32; ++i)
-                                    v[i] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + i * 64 + lane * 2));
+                                // planes are padded to whole tiles: pixels past the map are written too (never read as data)
+                                uint4* o = reinterpret_cast<uint4*>(P.out + (long)(g * 32 + hh * 16 + vrow) * P.out_plane + vrow0);
+                                o[0] = *reinterpret_cast<const uint4*>(stg + vo);
+                                o[1] = *reinterpret_cast<const uint4*>(stg + vo + 16);
                                 __syncwarp();
                             }
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
-                                *reinterpret_cast<__nv_bfloat16*>(stg + i * 64 + lane * 2) = __float2bfloat16(y0);
-                                *reinterpret_cast<__nv_bfloat16*>(stg + (i + 1) * 64 + lane * 2) = __float2bfloat16(y1);
-                                s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
-                            }
-                            __syncwarp();
-                            // planes are padded to whole tiles: pixels past the map are written too (never read as data)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<uint4*>(P.out + (long)(g * 32 + (lane >> 2) + 8 * j) * P.out_plane + vrow0) =
-                                    *reinterpret_cast<const uint4*>(stg + vo + j * 512);
-                            __syncwarp();
                         } else {
                             __nv_bfloat16* o = P.out + (long)(g * 32) * P.out_plane + pc;
                             if (P.addend != nullptr) {
@@ -778,18 +812,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                         const float* bs = sbias + g * 32;
                         if (P.out_vec && P.out_f32 == nullptr) {
                             uint8_t* stg = sm + stg_off + warp * EPI_STAGE;
-                            const uint32_t vo = (uint32_t)((lane >> 2) * 64 + (lane & 3) * 16);
+                            const uint32_t vo = (uint32_t)(vrow * 64 + (lane & 1) * 32);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                *reinterpret_cast<__nv_bfloat16*>(stg + i * 64 + lane * 2) = __float2bfloat16(lrelu(v[i] + bs[i], P.slope));
-                            __syncwarp();
+                            for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int n = g * 32 + (lane >> 2) + 8 * j;
-                                if (n < P.nout_store)
-                                    *reinterpret_cast<uint4*>(P.out + (long)n * P.out_plane + vrow0) = *reinterpret_cast<const uint4*>(stg + vo + j * 512);
+                                for (int j = 0; j < 16; ++j)
+                                    *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) =
+                                        __float2bfloat16(lrelu(v[16 * hh + j] + bs[16 * hh + j], P.slope));
+                                __syncwarp();
+                                const int n = g * 32 + hh * 16 + vrow;
+                                if (n < P.nout_store) {
+                                    uint4* o = reinterpret_cast<uint4*>(P.out + (long)n * P.out_plane + vrow0);
+                                    o[0] = *reinterpret_cast<const uint4*>(stg + vo);
+                                    o[1] = *reinterpret_cast<const uint4*>(stg + vo + 16);
+                                }
+                                __syncwarp();
                             }
-                            __syncwarp();
                         } else {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
@@ -884,8 +922,9 @@ static inline size_t gemm_smem_bytes_bulk(int NOUT, int K, bool gated, int* nraw
     const size_t fixed = gemm_smem_fixed(NOUT, K, true);
     if (nkb > MAXKB || fixed >= SMEM_CAP) return 0;
     const size_t avail = SMEM_CAP - fixed, slot = (size_t)RAW_SLOT + (gated ? GRAW_SLOT : 0);
-    for (int na = 3; na >= 2; --na) {
-        if (avail < (size_t)na * A_SLOT_BULK + 2 * slot) continue;
+    int best_raw = 0, best_na = 0;
+    for (int na = 2; na <= MAX_ASLOT; ++na) {
+        if (avail < (size_t)na * A_SLOT_BULK + 2 * slot) break;
         int nraw = (int)((avail - (size_t)na * A_SLOT_BULK) / slot);
         if (nraw > MAX_RAW) nraw = MAX_RAW;
         // The staging depth must be a multiple of the number of loader warps / converter groups (2): unit u and unit
@@ -893,9 +932,11 @@ static inline size_t gemm_smem_bytes_bulk(int NOUT, int K, bool gated, int* nraw
         // and a parity wait can never be two phases behind.  With an odd depth a loader can run ahead of the other
         // group's consumption and pass a wait on the aliased parity (found as a hang; tools/sim_pipeline.py).
         nraw &= ~1;
-        if (na == 3 && nraw == MAX_RAW && avail >= (size_t)MAX_ASLOT * A_SLOT_BULK + (size_t)MAX_RAW * slot) na = MAX_ASLOT;
-        *nraw_out = nraw; *na_out = na;
-        return fixed + (size_t)na * A_SLOT_BULK + (size_t)nraw * slot;
+        if (nraw >= best_raw && nraw >= 2) { best_raw = nraw; best_na = na; }   // deepest staging first, then operand slots
+    }
+    if (best_raw >= 2) {
+        *nraw_out = best_raw; *na_out = best_na;
+        return fixed + (size_t)best_na * A_SLOT_BULK + (size_t)best_raw * slot;
     }
     return 0;
 }
@@ -905,9 +946,13 @@ static inline size_t gemm_smem_bytes_bulk(int NOUT, int K, bool gated, int* nraw
 // whose planes are padded to whole tiles (so a full 256-byte row is always in bounds).
 static inline size_t plan_launch(GemmParams& P, int epi, bool allow_bulk) {
     const bool gated = P.seg.gate_seg >= 0;
-    bool bulk = allow_bulk && epi != EPI_POOL;
+    bool bulk = allow_bulk;
     const long npad = ((long)P.N + TILE_M - 1) / TILE_M * TILE_M;
-    for (int i = 0; i < 3 && bulk; ++i) {
+    if (epi == EPI_POOL) {          // 8-byte gather copies of one fp32 map
+        bulk = bulk && P.seg.kind[0] == 0 && P.seg.cend[0] == P.K && (reinterpret_cast<uintptr_t>(P.seg.src[0]) & 7) == 0 &&
+               (P.seg.plane[0] * 4) % 8 == 0 && (P.img_w & 1) == 0;
+    }
+    for (int i = 0; i < 3 && bulk && epi != EPI_POOL; ++i) {
         const int width = P.seg.cend[i] - (i ? P.seg.cend[i - 1] : 0);
         if (width <= 0) continue;
         const size_t esz = P.seg.kind[i] ? 2 : 4;

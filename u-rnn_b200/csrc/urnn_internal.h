@@ -27,6 +27,8 @@ int cgru_blend_launch(const CellWsView& w, const float* h, float* h_out, int F, 
 // channel row of a 128-pixel tile is a 16-byte aligned, in-bounds TMA bulk copy.
 long tc_pad_plane(long n);
 void tc_reset_direction();
+int tc_counters_begin(const urnn_cell_desc* d, void* cell_ws, size_t ws_bytes, cudaStream_t st);
+void tc_counters_end();
 size_t cgru_fwd_bf16_workspace(const urnn_cell_desc* d);
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st, long x_plane = 0);
