@@ -55,9 +55,11 @@ int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
     }
     const bool gated = P.seg.gate_seg >= 0;
     static const bool bulk_env = !(getenv("URNN_BULK") && getenv("URNN_BULK")[0] == '0');
-    const size_t smem = tc::plan_launch(P, epi, bulk_env);
+    static const bool bias_mma_env = getenv("URNN_BIAS_MMA") && getenv("URNN_BIAS_MMA")[0] == '1';
+    const size_t smem = tc::plan_launch(P, epi, bulk_env, bias_mma_env);
     if (smem == 0) { set_error("tc gemm: weights %dx%d do not fit in shared memory", P.NOUT, P.K); return URNN_E_UNSUPPORTED; }
-    static const bool rev_env = !(getenv("URNN_REVERSE") && getenv("URNN_REVERSE")[0] == '0');
+    // alternating sweep directions (L2 reuse between consecutive kernels) measured no gain at 500 x 500: off by default
+    static const bool rev_env = getenv("URNN_REVERSE") && getenv("URNN_REVERSE")[0] == '1';
     P.reverse = rev_env ? g_dir : 0; g_dir ^= 1;
     P.dbg = nullptr;
     int ntiles = (P.N + tc::TILE_M - 1) / tc::TILE_M;
@@ -75,7 +77,7 @@ int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
 void tc_params_defaults(tc::GemmParams& P) {
     P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
     for (int i = 0; i < 3; ++i) { P.seg.src[i] = nullptr; P.seg.cend[i] = 0; P.seg.kind[i] = 0; P.seg.plane[i] = 0; }
-    P.seg.gate_plane = 0; P.bulk = 0; P.nraw = 0; P.na = 0; P.reverse = 0; P.nstage = 0;
+    P.seg.gate_plane = 0; P.bulk = 0; P.nraw = 0; P.na = 0; P.reverse = 0; P.nstage = 0; P.bias_mma = 0; P.out_vec = 0;
     P.w_ks = 1; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0; P.bias = nullptr; P.nbias = 0;
     P.out = nullptr; P.out_f32 = nullptr; P.addend = nullptr; P.nstat = 0; P.slope = 0.f; P.img_w = 0; P.n_base = 0;
     P.sink = StatSink{nullptr, nullptr, nullptr, 0, 0, CommDev{1, 0, {nullptr}, {nullptr}, nullptr}};

@@ -39,7 +39,7 @@ constexpr int NPROD = 512;            // producer threads
 constexpr int NEPI = 256;             // epilogue threads (simt mode): warp w owns TMEM lanes 32*(w%4).. and column groups w/4, w/4+2, ..
 constexpr int NEPI_BULK = 512;        // bulk mode: warps 8-15 join the epilogue (column groups w/4, w/4+4), warps 16-23 convert
 constexpr int NLOADW = 2;             // bulk mode: loader warps (cp.async row copies), alternating units
-constexpr int NTHREADS = NEPI + NPROD + 32 + 32 * NLOADW;
+constexpr int NTHREADS = NEPI + NPROD + 128;   // 28 warps = 7 whole warpgroups (setmaxnreg works per warpgroup); warp 27 idles
 constexpr int MMA_WARP = (NEPI + NPROD) / 32;
 constexpr int LOAD_WARP0 = MMA_WARP + 1;    // bulk mode: first loader warp
 constexpr int UNIT_K = 32;            // bulk mode: channels per unit
@@ -62,20 +62,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// try_wait returns after a short hardware time-out, so a bare loop polls every ~40 cycles: with 16 converter warps
-// waiting for data that was 53 % of all issued instructions (ncu source view) and starved the epilogue warps.
-// Waits that have slack therefore back off with nanosleep after a failed poll.
+// A bare try_wait loop polls every ~25-40 cycles (the default hardware time-out is short, and nanosleep(32) returns
+// almost immediately): with 16 waiting warps that was 43-53 % of all issued instructions (ncu source view,
+// profiles/) and starved the warps doing real work.  The suspend-time hint lets the hardware park the thread until the
+// phase completes (or the hint expires), so a wait costs a handful of instructions.
 template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     for (;;) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
         if (done) break;
-        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
     }
 }
 // 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); bytes past `src_bytes` (0..16) are zero-filled and
@@ -91,6 +91,12 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Register re-partitioning between warp roles (per warpgroup of 4 warps).  Launch: 28 warps x 72 = 64512 registers.
+// epilogue warps take 80 (their 32-value accumulator slice + staging addresses spilled at 72), the MMA / loader
+// warpgroup gives back to 40:  bulk mode 16x80 + 8x72 + 4x40 (x32 lanes) = 64512; simt mode 8x80 + 16x72 + 4x40.
+__device__ __forceinline__ void regs_epilogue() { asm volatile("setmaxnreg.inc.sync.aligned.u32 80;" ::: "memory"); }
+__device__ __forceinline__ void regs_converter() {}   // converters keep the launch allocation (72)
+__device__ __forceinline__ void regs_control() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -230,6 +236,8 @@ struct GemmParams {
     int nstage;                              // simt mode: K-block ring depth (64-channel slots)
     int bulk, nraw, na;                      // bulk mode: on/off, staging ring depth, operand ring depth (32-channel slots)
     int reverse;                             // walk the tiles from the last to the first (L2 reuse between sweeps)
+    int bias_mma;                            // bulk mode: the bias rides in the GEMM as two extra channels of ones (weights bf16 hi + lo
+                                             // parts of the bias), so the epilogue has no bias loads / adds
     int out_vec;                             // bf16 output (and addend) planes are padded to whole tiles and 16-byte aligned:
                                              // the epilogue moves them as 16-byte row pieces through a per-warp staging tile
     int tmem_cols;                           // power of two >= 2 * NOUT
@@ -266,7 +274,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NOUT = P.NOUT, K = P.K, N = P.N;
     if (P.dbg && blockIdx.x == 0 && tid == 0) { unsigned t_; asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t_)); P.dbg[148 * 16 + 6 * 64] = t_; }
-    const int Kp = (K + 15) & ~15;                          // padded to the MMA K
+    const int Kb = K + (P.bias_mma ? 2 : 0);                // + the two bias channels
+    const int Kp = (Kb + 15) & ~15;                         // padded to the MMA K
     const int nkb = (Kp + KBLK - 1) / KBLK;                 // K blocks per tile
     const int last_k = Kp - (nkb - 1) * KBLK;               // valid (padded) channels in the last block
     const int wblk_bytes = NOUT * 128;
@@ -324,6 +333,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             } else {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim && n < P.nout_store) ? __ldg(wrow + (long)(k0 + u) * ks) : 0.f;
+                if (P.bias_mma && n < P.nbias && k0 <= K + 1 && k0 + 8 > K) {      // columns K, K+1: bias = hi + lo in bf16
+                    const float b = __ldg(P.bias + n);
+                    const float hi = __bfloat162float(__float2bfloat16(b));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { if (k0 + u == K) v[u] = hi; if (k0 + u == K + 1) v[u] = b - hi; }
+                }
             }
         };
         auto wstore = [&](int idx, const float (&v)[8]) {
@@ -362,6 +377,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 e.gptr = reinterpret_cast<const char*>(S.gate_pre) + (long)(S.gate_ch0 + cc) * S.gate_plane * 2;
                 e.meta |= 4 | ((S.gate_ch0 + cc) << 8);
             }
+        } else if (k < Kb) {
+            e.meta = 8;                                      // bias channel: constant one
         }
         ctab[k] = e;
     }
@@ -534,6 +551,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 commit(kb, stage, b);
             }
         } else {
+            regs_converter();
             // ---- bulk mode: staging (raw rows landed by cp.async) -> bf16 swizzled operand slot.  Unit = 32 channels x 128
             // pixels; a thread (ch0 = 0..7) converts 8 pixels of channels ch0 + 8c, c = 0..3.  Operand slot: 1024-byte
             // atoms of 8 channels x 64 pixels, atom(mblk, kblk) at mblk*4096 + kblk*1024 -> chunk c is K-atom c.
@@ -554,6 +572,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 const uint8_t* rawp = sm + raw_off + rs * raw_slot_bytes;
                 mbar_wait<96>(rfull0 + 8 * rs, rph);
                 uint4 pk[4];
+                // fast paths: my four channels are of one kind and the tile is whole -> all shared loads are issued
+                // back to back, without per-channel control flow (a converter warp is latency-bound, not issue-bound)
+                const ChanEnt* ent = ctab + kb * UNIT_K + ch0;
+                const int m0 = ent[0].meta, m1 = ent[8].meta, m2 = ent[16].meta, m3 = ent[24].meta;
+                const int kind_and = m0 & m1 & m2 & m3 & 15, kind_or = (m0 | m1 | m2 | m3) & 15;
+                if (kind_and == kind_or && nv == 8 && (kind_or == 1 || kind_or == 3 || (GATED && kind_or == 5))) {
+                    if (kind_or == 3) {
+                        uint4 w[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) w[c] = *reinterpret_cast<const uint4*>(rawp + (ch0 + 8 * c) * RAW_ROW + px8 * 16);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) pk[c] = w[c];                 // already bf16: a plain copy
+                    } else if (!GATED || kind_or == 1) {
+                        float4 f[4][2];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint8_t* r = rawp + (ch0 + 8 * c) * RAW_ROW + px8 * 32;
+                            f[c][0] = *reinterpret_cast<const float4*>(r + (swp ? 16 : 0));
+                            f[c][1] = *reinterpret_cast<const float4*>(r + (swp ? 0 : 16));
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 lo = swp ? f[c][1] : f[c][0], hi = swp ? f[c][0] : f[c][1];
+                            pk[c] = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+                        }
+                    } else {
+                        // reset-gated rows: two channels at a time (register budget)
+#pragma unroll
+                        for (int c2 = 0; c2 < 4; c2 += 2) {
+                            float4 f[2][2]; uint4 g[2]; float2 aff[2];
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const uint8_t* r = rawp + (ch0 + 8 * (c2 + c)) * RAW_ROW + px8 * 32;
+                                f[c][0] = *reinterpret_cast<const float4*>(r + (swp ? 16 : 0));
+                                f[c][1] = *reinterpret_cast<const float4*>(r + (swp ? 0 : 16));
+                                g[c] = *reinterpret_cast<const uint4*>(rawp + RAW_SLOT + (ch0 + 8 * (c2 + c)) * 256 + px8 * 16);
+                                aff[c] = *reinterpret_cast<const float2*>(&ent[8 * (c2 + c)].sc);
+                            }
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                float gv[8];
+                                unpack_bf16x2(g[c].x, gv[0], gv[1]); unpack_bf16x2(g[c].y, gv[2], gv[3]);
+                                unpack_bf16x2(g[c].z, gv[4], gv[5]); unpack_bf16x2(g[c].w, gv[6], gv[7]);
+                                const float4 lo = swp ? f[c][1] : f[c][0], hi = swp ? f[c][0] : f[c][1];
+                                const float a = aff[c].x, b = aff[c].y;
+                                pk[c2 + c] = make_uint4(
+                                    pack_bf16(lo.x * sigmoid_fast(fmaf(gv[0], a, b)), lo.y * sigmoid_fast(fmaf(gv[1], a, b))),
+                                    pack_bf16(lo.z * sigmoid_fast(fmaf(gv[2], a, b)), lo.w * sigmoid_fast(fmaf(gv[3], a, b))),
+                                    pack_bf16(hi.x * sigmoid_fast(fmaf(gv[4], a, b)), hi.y * sigmoid_fast(fmaf(gv[5], a, b))),
+                                    pack_bf16(hi.z * sigmoid_fast(fmaf(gv[6], a, b)), hi.w * sigmoid_fast(fmaf(gv[7], a, b))));
+                            }
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int ch = ch0 + 8 * c;
@@ -589,6 +661,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                             for (int q = 0; q < 8; ++q) v[q] = (q < nv) ? v[q] : 0.f;
                         }
                         pk[c] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    } else if (meta & 8) {
+                        pk[c] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);   // bf16 ones
                     }
                 }
                 mbar_arrive(rempty0 + 8 * rs);               // staging slot consumed (values are in registers)
@@ -601,7 +675,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 if (warp == NEPI_BULK / 32 && kb == nu - 1) { TC_TRACE(1, trace_i); ++trace_i; }
             }
         }
-    } else if (warp >= LOAD_WARP0) {
+    } else if (warp >= MMA_WARP) {
+      regs_control();
+      if (warp >= LOAD_WARP0 && warp < LOAD_WARP0 + NLOADW) {
         // =========================================================================== loaders (bulk mode)
         // Loader warp l streams the units u = l (mod NLOADW): per channel row one warp-wide 16-byte cp.async (512 B of an
         // fp32 row; a bf16 row, 256 B, uses lanes 0-15), plus the row of reset-gate pre-activations for gated channels.
@@ -671,7 +747,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 cp_async_arrive(rfull0 + 8 * rs);
             }
         }
-    } else if (warp == MMA_WARP) {
+      } else if (warp == MMA_WARP) {
         // =========================================================================== MMA issuer
         // every lane follows the pipeline (waits), lane 0 alone issues tcgen05.mma / tcgen05.commit
         const uint32_t idesc = instr_desc_bf16(NOUT);
@@ -711,8 +787,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             TC_TRACE(2, (tile - (int)blockIdx.x) / (int)gridDim.x);
             as ^= 1; if (as == 0) aphase ^= 1;
         }
+      }
     } else {
-        // =========================================================================== epilogue (warps 0-7)
+        // =========================================================================== epilogue (warps 0-7; 0-15 in bulk mode)
+        regs_epilogue();
         // warp w: TMEM lanes 32*(w&3).. (pixels), 32-column groups g = (w>>2), (w>>2)+2, ... (output channels)
         float st_s[MAXG / 2], st_ss[MAXG / 2];
 #pragma unroll
@@ -776,10 +854,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                                         v[16 * hh + j] += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + j * 64 + lane * 2));
                                     __syncwarp();
                                 }
+                                if (!P.bias_mma) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[16 * hh + j] += bs[16 * hh + j];
+                                }
 #pragma unroll
                                 for (int j = 0; j < 16; j += 2) {
                                     const int i = 16 * hh + j;
-                                    const float y0 = v[i] + bs[i], y1 = v[i + 1] + bs[i + 1];
+                                    const float y0 = v[i], y1 = v[i + 1];
                                     *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) = __float2bfloat16(y0);
                                     *reinterpret_cast<__nv_bfloat16*>(stg + (j + 1) * 64 + lane * 2) = __float2bfloat16(y1);
                                     s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
@@ -815,10 +897,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                             const uint32_t vo = (uint32_t)(vrow * 64 + (lane & 1) * 32);
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
+                                if (!P.bias_mma) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[16 * hh + j] += bs[16 * hh + j];
+                                }
 #pragma unroll
                                 for (int j = 0; j < 16; ++j)
-                                    *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) =
-                                        __float2bfloat16(lrelu(v[16 * hh + j] + bs[16 * hh + j], P.slope));
+                                    *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) = __float2bfloat16(lrelu(v[16 * hh + j], P.slope));
                                 __syncwarp();
                                 const int n = g * 32 + hh * 16 + vrow;
                                 if (n < P.nout_store) {
@@ -944,7 +1029,7 @@ static inline size_t gemm_smem_bytes_bulk(int NOUT, int K, bool gated, int* nraw
 // Host side: choose the producer mode and ring depths for a filled-in GemmParams; returns the dynamic shared memory
 // size (0: the weights do not fit).  Bulk mode needs 16-byte aligned channel rows: fp32 maps with N % 4 == 0, bf16 maps
 // whose planes are padded to whole tiles (so a full 256-byte row is always in bounds).
-static inline size_t plan_launch(GemmParams& P, int epi, bool allow_bulk) {
+static inline size_t plan_launch(GemmParams& P, int epi, bool allow_bulk, bool allow_bias_mma = false) {
     const bool gated = P.seg.gate_seg >= 0;
     bool bulk = allow_bulk;
     const long npad = ((long)P.N + TILE_M - 1) / TILE_M * TILE_M;
@@ -963,11 +1048,21 @@ static inline size_t plan_launch(GemmParams& P, int epi, bool allow_bulk) {
         bulk = (reinterpret_cast<uintptr_t>(P.seg.gate_pre) & 15) == 0 && (P.seg.gate_plane * 2) % 16 == 0 && P.seg.gate_plane >= npad;
     int nstage = 0, nraw = 0, na = 0;
     size_t smem = 0;
-    if (bulk) { smem = gemm_smem_bytes_bulk(P.NOUT, P.K, gated, &nraw, &na); if (smem == 0) bulk = false; }
-    if (!bulk) smem = gemm_smem_bytes(P.NOUT, P.K, &nstage);
-    P.nstage = nstage; P.bulk = bulk ? 1 : 0; P.nraw = nraw; P.na = na;
+    // out_vec decides whether the staged epilogue (the one that can drop its bias adds) is used at all
     P.out_vec = (P.out != nullptr && P.out_plane >= npad && P.out_plane % 8 == 0 && (reinterpret_cast<uintptr_t>(P.out) & 15) == 0 &&
                  (P.addend == nullptr || (reinterpret_cast<uintptr_t>(P.addend) & 15) == 0) && (epi == EPI_GN || epi == EPI_LRELU)) ? 1 : 0;
+    P.bias_mma = 0;
+    // (off by default: the hi + lo bf16 split changes results in the last bit relative to the epilogue add, and it only
+    //  pays when the two channels fit into existing padding; URNN_BIAS_MMA=1 enables it)
+    if (allow_bias_mma && bulk && P.out_vec && P.out_f32 == nullptr && P.bias != nullptr) {
+        // only when the two extra channels fit into the padding of the last 32-channel unit (no extra unit per tile)
+        const int nu0 = (((P.K + 15) & ~15) + UNIT_K - 1) / UNIT_K, nu1 = (((P.K + 2 + 15) & ~15) + UNIT_K - 1) / UNIT_K;
+        if (nu1 == nu0) smem = gemm_smem_bytes_bulk(P.NOUT, P.K + 2, gated, &nraw, &na);
+        if (smem != 0 && nraw >= 4) P.bias_mma = 1; else smem = 0;
+    }
+    if (bulk && !P.bias_mma) { smem = gemm_smem_bytes_bulk(P.NOUT, P.K, gated, &nraw, &na); if (smem == 0) bulk = false; }
+    if (!bulk) smem = gemm_smem_bytes(P.NOUT, P.K, &nstage);
+    P.nstage = nstage; P.bulk = bulk ? 1 : 0; P.nraw = nraw; P.na = na;
     int cols = 32;
     while (cols < 2 * P.NOUT) cols <<= 1;
     P.tmem_cols = cols;
