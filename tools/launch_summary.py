@@ -7,11 +7,11 @@ rows = [(r['Kernel Name'], r.get('Grid Size'), float(r['Metric Value']) / 1e3) f
 names = [re.sub(r'urnn::', '', re.sub(r'\(.*', '', n)) for n, _, _ in rows]
 start = None
 for i in range(len(rows) - 2):
-    if 'head_kernel<3>' in names[i]:
+    if 'head_kernel<3>' in names[i] or 'head_stage_kernel<3' in names[i]:
         start = i + 1
         break
 end = start
-while end < len(rows) and 'head_kernel<3>' not in names[end]:
+while end < len(rows) and 'head_kernel<3>' not in names[end] and 'head_stage_kernel<3' not in names[end]:
     end += 1
 tot = 0.0
 for i in range(start, end + 1):

@@ -1,6 +1,7 @@
 // urnn_fp32.cu -- URNN_MATH_FP32 forward path: ConvGRU cell passes, stage stems, head, on the fp32 pixel-GEMM.
 // Host-side orchestration only enqueues kernels on the caller's stream (graph-capturable).
 #include "pixgemm.cuh"
+#include <stdlib.h>
 #include "head.cuh"
 #include "urnn_internal.h"
 
@@ -168,7 +169,7 @@ int deconv2x2_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, float slope, const
 }
 
 // ------------------------------------------------------------------------------------------------ head
-struct HeadWs { float2* partial; double2* total; unsigned* counter; int gx; };
+struct HeadWs { float2* partial; double2* total; unsigned* counter; int gx; float *bufA, *bufB; };
 static size_t head_ws_layout(int H, int W, void* ws, size_t ws_bytes, HeadWs* out) {
     long N = (long)H * W;
     int gx = (int)((N + 127) / 128);
@@ -177,6 +178,8 @@ static size_t head_ws_layout(int H, int W, void* ws, size_t ws_bytes, HeadWs* ou
     w.counter = a.take<unsigned>(64);
     w.total = a.take<double2>(8);
     w.partial = a.take<float2>((size_t)5 * gx);
+    w.bufA = a.take<float>((size_t)16 * N);              // un-normalised cls / reg branch maps between the staged sweeps
+    w.bufB = a.take<float>((size_t)16 * N);
     if (out) *out = w;
     return align_up(a.off, 256);
 }
@@ -195,6 +198,22 @@ int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, cons
     hd.count = 16.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);
     hd.sink = StatSink{w.partial, w.total, w.counter, 5, w.gx, comm};
     head_kernel<0><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
+    static const bool staged = !(getenv("URNN_HEAD_STAGED") && getenv("URNN_HEAD_STAGED")[0] == '0');
+    if (staged) {
+        // one LayerNorm level per sweep, starting from the previous level's stored pre-norm maps (head.cuh)
+        static const int px = (getenv("URNN_HEAD_PX") && getenv("URNN_HEAD_PX")[0] == '1') ? 1 : 2;   // pixels per thread
+        const int gx2 = (int)((N + 128 * px - 1) / (128 * px));
+        if (px == 2) {
+            head_stage_kernel<1, 2><<<gx2, 128, 0, st>>>(hd, feat, w.bufA, w.bufB, out, (int)N); URNN_LAUNCH_CHECK();
+            head_stage_kernel<2, 2><<<gx2, 128, 0, st>>>(hd, feat, w.bufA, w.bufB, out, (int)N); URNN_LAUNCH_CHECK();
+            head_stage_kernel<3, 2><<<gx2, 128, 0, st>>>(hd, feat, w.bufA, w.bufB, out, (int)N); URNN_LAUNCH_CHECK();
+        } else {
+            head_stage_kernel<1, 1><<<gx2, 128, 0, st>>>(hd, feat, w.bufA, w.bufB, out, (int)N); URNN_LAUNCH_CHECK();
+            head_stage_kernel<2, 1><<<gx2, 128, 0, st>>>(hd, feat, w.bufA, w.bufB, out, (int)N); URNN_LAUNCH_CHECK();
+            head_stage_kernel<3, 1><<<gx2, 128, 0, st>>>(hd, feat, w.bufA, w.bufB, out, (int)N); URNN_LAUNCH_CHECK();
+        }
+        return URNN_OK;
+    }
     head_kernel<1><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
     head_kernel<2><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
     head_kernel<3><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
