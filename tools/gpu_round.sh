@@ -9,7 +9,7 @@ echo "== selftest quick" ; timeout 120 tools/bin/tc_selftest quick > $OUT/selfte
 if [ $RC -ne 0 ]; then echo "selftest failed: stopping"; tail -30 $OUT/selftest_quick.log; exit 1; fi
 echo "== pytest gpu"; timeout 600 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "rc=$?"; tail -4 $OUT/pytest_gpu.log
 echo "== bench (watchdog 150 s)"; timeout 200 python bench.py --watchdog 150 > $OUT/bench_n1.json 2> $OUT/bench_n1.err; echo "rc=$?"; cat $OUT/bench_n1.json; tail -30 $OUT/bench_n1.err
-for cfg in "URNN_HEAD_PX=1"; do
+for cfg in "URNN_WIMG=0"; do
   echo "== bench value-only $cfg"
   env $cfg timeout 100 python bench.py --value-only --steps 180 --watchdog 80 > $OUT/bench_$cfg.json 2> $OUT/bench_$cfg.err; echo "rc=$?"; cat $OUT/bench_$cfg.json; grep -v "^\[bench" $OUT/bench_$cfg.err | tail -12
 done

@@ -165,6 +165,7 @@ struct EdPlan {
     float *s[3], *up3, *up2, *feat;       // stem outputs, deconv outputs, decoder features
     void* cell_ws; size_t cell_ws_bytes;
     void* head_ws; size_t head_ws_bytes;
+    void* wimg; size_t wimg_bytes;
     size_t total;
 };
 
@@ -199,6 +200,8 @@ static int ed_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, EdPlan* pl)
     }
     pl->cell_ws_bytes = cw;
     pl->cell_ws = a.take<char>(cw);
+    pl->wimg_bytes = (d->math == URNN_MATH_BF16) ? ((size_t)4 << 20) : 0;       // bf16 weight images of the step's GEMMs
+    pl->wimg = a.take<char>(pl->wimg_bytes);
     pl->head_ws_bytes = urnn_head_fwd_workspace_bytes(d->H, d->W);
     pl->head_ws = a.take<char>(pl->head_ws_bytes);
     pl->total = align_up(a.off, 256);
@@ -232,30 +235,38 @@ static int ed_step_impl(const urnn_ed_desc* d, const urnn_ed_params* p, const St
         // tcgen05 route: stem outputs that only feed GEMMs are kept as bf16 maps (the consumer would round them anyway)
         __nv_bfloat16* sb[3] = {(__nv_bfloat16*)pl.s[0], (__nv_bfloat16*)pl.s[1], (__nv_bfloat16*)pl.s[2]};
         __nv_bfloat16 *up3 = (__nv_bfloat16*)pl.up3, *up2 = (__nv_bfloat16*)pl.up2;
-        const float* cur = input; int cin = s1.cin;
         long np[3];
         for (int k = 0; k < 3; ++k) np[k] = tc_pad_plane((long)pl.h[k] * pl.w[k]);
-        tc_reset_direction();
+        // the launch sequence of the step (stems, 6 cells, deconvs); run once to record the GEMM weights, once for real
+        auto body = [&]() -> int {
+            tc_reset_direction();
+            const float* cur = input; int cin = s1.cin;
+            for (int k = 0; k < 3; ++k) {
+                int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
+                URNN_TRY(conv1x1_lrelu_fwd_tc(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, 0,
+                                              k == 0 ? s1.w : p->enc_stem_w[k], k == 0 ? s1.w_ld : (long)cin,
+                                              k == 0 ? s1.b : p->enc_stem_b[k], sb[k], nullptr, st, 0, np[k]));
+                URNN_TRY(check_cell(&pl.enc[k], &p->enc_cell[k], nullptr, sin[k], sout[k]));
+                URNN_TRY(cgru_fwd_bf16(&pl.enc[k], &p->enc_cell[k], sb[k], 1, nullptr, sin[k], sout[k], pl.cell_ws, pl.cell_ws_bytes, st, np[k]));
+                cur = sout[k]; cin = d->enc_gru[k];
+            }
+            URNN_TRY(cgru_fwd_bf16(&pl.dec[0], &p->dec_cell[0], nullptr, 0, sout[2], sin[3], sout[3], pl.cell_ws, pl.cell_ws_bytes, st));
+            URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[0], d->dec_conv[0], pl.h[2], pl.w[2], sl, sout[3], 0, p->dec_stem_w[0],
+                                            p->dec_stem_b[0], up3, nullptr, st, np[1]));
+            URNN_TRY(cgru_fwd_bf16(&pl.dec[1], &p->dec_cell[1], up3, 1, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, st, np[1]));
+            URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, sout[4], 0, p->dec_stem_w[1],
+                                            p->dec_stem_b[1], up2, nullptr, st, np[0]));
+            URNN_TRY(cgru_fwd_bf16(&pl.dec[2], &p->dec_cell[2], up2, 1, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, st, np[0]));
+            URNN_TRY(conv1x1_lrelu_fwd_tc(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], 0, p->dec_stem_w[2], d->dec_gru[2],
+                                          p->dec_stem_b[2], nullptr, pl.feat, st));
+            return URNN_OK;
+        };
         URNN_TRY(tc_counters_begin(&pl.enc[0], pl.cell_ws, pl.cell_ws_bytes, st));
-        struct CountersGuard { ~CountersGuard() { tc_counters_end(); } } counters_guard;
-        for (int k = 0; k < 3; ++k) {
-            int hin = (k == 0) ? pl.h[0] : pl.h[k - 1], win = (k == 0) ? pl.w[0] : pl.w[k - 1];
-            URNN_TRY(conv1x1_lrelu_fwd_tc(cin, d->enc_conv[k], hin, win, k == 0 ? 1 : 2, sl, cur, 0,
-                                          k == 0 ? s1.w : p->enc_stem_w[k], k == 0 ? s1.w_ld : (long)cin,
-                                          k == 0 ? s1.b : p->enc_stem_b[k], sb[k], nullptr, st, 0, np[k]));
-            URNN_TRY(check_cell(&pl.enc[k], &p->enc_cell[k], nullptr, sin[k], sout[k]));
-            URNN_TRY(cgru_fwd_bf16(&pl.enc[k], &p->enc_cell[k], sb[k], 1, nullptr, sin[k], sout[k], pl.cell_ws, pl.cell_ws_bytes, st, np[k]));
-            cur = sout[k]; cin = d->enc_gru[k];
-        }
-        URNN_TRY(cgru_fwd_bf16(&pl.dec[0], &p->dec_cell[0], nullptr, 0, sout[2], sin[3], sout[3], pl.cell_ws, pl.cell_ws_bytes, st));
-        URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[0], d->dec_conv[0], pl.h[2], pl.w[2], sl, sout[3], 0, p->dec_stem_w[0],
-                                        p->dec_stem_b[0], up3, nullptr, st, np[1]));
-        URNN_TRY(cgru_fwd_bf16(&pl.dec[1], &p->dec_cell[1], up3, 1, sout[1], sin[4], sout[4], pl.cell_ws, pl.cell_ws_bytes, st, np[1]));
-        URNN_TRY(deconv2x2_lrelu_fwd_tc(d->dec_gru[1], d->dec_conv[1], pl.h[1], pl.w[1], sl, sout[4], 0, p->dec_stem_w[1],
-                                        p->dec_stem_b[1], up2, nullptr, st, np[0]));
-        URNN_TRY(cgru_fwd_bf16(&pl.dec[2], &p->dec_cell[2], up2, 1, sout[0], sin[5], sout[5], pl.cell_ws, pl.cell_ws_bytes, st, np[0]));
-        URNN_TRY(conv1x1_lrelu_fwd_tc(d->dec_gru[2], 16, pl.h[0], pl.w[0], 1, sl, sout[5], 0, p->dec_stem_w[2], d->dec_gru[2],
-                                      p->dec_stem_b[2], nullptr, pl.feat, st));
+        struct StepGuard { ~StepGuard() { tc_counters_end(); tc_wimg_off(); } } step_guard;
+        tc_wimg_begin_record(pl.wimg, pl.wimg_bytes);
+        URNN_TRY(body());
+        URNN_TRY(tc_wimg_convert(st));
+        URNN_TRY(body());
         return urnn_head_fwd(d->H, d->W, d->cls_thred, d->ln_eps, sl, &p->head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, stream);
     }
 #endif

@@ -47,7 +47,49 @@ static int tc_launch_t(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st
     return URNN_OK;
 }
 
+// ---- weight images of a whole time step (see tc::wimg_kernel): the step driver runs its launch sequence twice, first in
+// RECORD mode (GEMM launches only note their weights and get an arena offset; nothing else runs), converts all images
+// with one kernel, then in REPLAY mode (each GEMM finds its image by position).
+enum { WIMG_OFF = 0, WIMG_RECORD = 1, WIMG_REPLAY = 2 };
+struct WImgState { int mode, idx; size_t cap, used; tc::WImgBatch batch; };
+static thread_local WImgState g_wimg = {WIMG_OFF, 0, 0, 0, {}};
+bool tc_recording() { return g_wimg.mode == WIMG_RECORD; }
+void tc_wimg_begin_record(void* arena, size_t cap) {
+    g_wimg.mode = WIMG_RECORD; g_wimg.idx = 0; g_wimg.cap = cap; g_wimg.used = 0; g_wimg.batch.n = 0; g_wimg.batch.base = (char*)arena;
+}
+void tc_wimg_off() { g_wimg.mode = WIMG_OFF; }
+// ends RECORD: converts the recorded weights (one launch) and switches to REPLAY; on overflow images stay off
+int tc_wimg_convert(cudaStream_t st) {
+    static const bool env_on = !(getenv("URNN_WIMG") && getenv("URNN_WIMG")[0] == '0');
+    static const bool bias_mma_env = getenv("URNN_BIAS_MMA") && getenv("URNN_BIAS_MMA")[0] == '1';
+    if (!env_on || bias_mma_env || g_wimg.batch.n == 0 || g_wimg.batch.n > tc::WIMG_MAX || g_wimg.used > g_wimg.cap) { g_wimg.mode = WIMG_OFF; return URNN_OK; }
+    tc::wimg_kernel<<<dim3(24, g_wimg.batch.n), 256, 0, st>>>(g_wimg.batch);
+    URNN_LAUNCH_CHECK();
+    g_wimg.mode = WIMG_REPLAY; g_wimg.idx = 0;
+    return URNN_OK;
+}
+
 int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
+    P.wimg = nullptr;
+    if (g_wimg.mode == WIMG_RECORD) {
+        if (g_wimg.batch.n < tc::WIMG_MAX) {
+            tc::WImgSpec& S = g_wimg.batch.s[g_wimg.batch.n];
+            S.W = P.W; S.w_ld = P.w_ld; S.w_ks = P.w_ks; S.nrow1 = P.nrow1; S.W2 = P.W2; S.w2_ld = P.w2_ld; S.k2 = P.k2;
+            S.NOUT = P.NOUT; S.K = P.K; S.nout_store = P.nout_store; S.off = g_wimg.used;
+            g_wimg.used += align_up(tc::wimg_bytes(P.NOUT, P.K), 256);
+        }
+        ++g_wimg.batch.n;
+        return URNN_OK;
+    }
+    if (g_wimg.mode == WIMG_REPLAY) {
+        if (g_wimg.idx < g_wimg.batch.n) {
+            const tc::WImgSpec& S = g_wimg.batch.s[g_wimg.idx];
+            if (S.W == P.W && S.W2 == P.W2 && S.NOUT == P.NOUT && S.K == P.K && S.nrow1 == P.nrow1 && S.k2 == P.k2 &&
+                S.w_ld == P.w_ld && S.w_ks == P.w_ks && S.nout_store == P.nout_store)
+                P.wimg = g_wimg.batch.base + S.off;
+        }
+        ++g_wimg.idx;
+    }
     if (g_num_sms == 0) {
         int dev = 0;
         URNN_CUDA(cudaGetDevice(&dev));
@@ -77,7 +119,7 @@ int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
 void tc_params_defaults(tc::GemmParams& P) {
     P.seg.gate_seg = -1; P.seg.gate_ch0 = 0; P.seg.gate_pre = nullptr; P.seg.gate_scale = nullptr; P.seg.gate_shift = nullptr;
     for (int i = 0; i < 3; ++i) { P.seg.src[i] = nullptr; P.seg.cend[i] = 0; P.seg.kind[i] = 0; P.seg.plane[i] = 0; }
-    P.seg.gate_plane = 0; P.bulk = 0; P.nraw = 0; P.na = 0; P.reverse = 0; P.nstage = 0; P.bias_mma = 0; P.out_vec = 0;
+    P.seg.gate_plane = 0; P.bulk = 0; P.nraw = 0; P.na = 0; P.reverse = 0; P.nstage = 0; P.bias_mma = 0; P.out_vec = 0; P.wimg = nullptr;
     P.w_ks = 1; P.W2 = nullptr; P.w2_ld = 0; P.k2 = 0; P.bias = nullptr; P.nbias = 0;
     P.out = nullptr; P.out_f32 = nullptr; P.addend = nullptr; P.nstat = 0; P.slope = 0.f; P.img_w = 0; P.n_base = 0;
     P.sink = StatSink{nullptr, nullptr, nullptr, 0, 0, CommDev{1, 0, {nullptr}, {nullptr}, nullptr}};
@@ -260,6 +302,7 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     URNN_TRY(tc_launch(P, tc::EPI_GN, st));
 
     // ---- sweep C
+    if (tc_recording()) return URNN_OK;
     {
         static const bool pdl = !(getenv("URNN_PDL") && getenv("URNN_PDL")[0] == '0');
         const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0;

@@ -236,6 +236,8 @@ struct GemmParams {
     int nstage;                              // simt mode: K-block ring depth (64-channel slots)
     int bulk, nraw, na;                      // bulk mode: on/off, staging ring depth, operand ring depth (32-channel slots)
     int reverse;                             // walk the tiles from the last to the first (L2 reuse between sweeps)
+    const void* wimg;                        // optional pre-converted weight image (bf16, swizzled, exactly the shared-memory layout):
+                                             // the prologue then copies nkb*NOUT*128 bytes instead of converting fp32 weights
     int bias_mma;                            // bulk mode: the bias rides in the GEMM as two extra channels of ones (weights bf16 hi + lo
                                              // parts of the bias), so the epilogue has no bias loads / adds
     int out_vec;                             // bf16 output (and addend) planes are padded to whole tiles and 16-byte aligned:
@@ -316,7 +318,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     } else {
         for (int i = tid; i < NOUT; i += NTHREADS) sbias[i] = (i < P.nbias) ? __ldg(P.bias + i) : 0.f;
     }
-    {
+    if (P.wimg != nullptr) {
+        // image prepared once per step by wimg_kernel: plain asynchronous 16-byte copies, rotated per CTA so that the
+        // 148 CTAs do not ask the same L2 lines at the same moment
+        const int nvec = nkb * (wblk_bytes >> 4);
+        const int rot = (int)((blockIdx.x * 41u) % (unsigned)(nvec >> 5)) << 5;
+        const char* src = reinterpret_cast<const char*>(P.wimg);
+        for (int i = tid; i < nvec; i += NTHREADS) {
+            const int j = i + rot >= nvec ? i + rot - nvec : i + rot;
+            cp_async16(base + w_off + (uint32_t)j * 16u, src + (size_t)j * 16u, 16u);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
         // 16-byte chunks (8 bf16) of the swizzled image; two chunks per thread and iteration so that four 16-byte loads
         // are in flight (the prologue is latency-bound: weights come from L2)
         const int chunks_per_row = nkb * 8, total = NOUT * chunks_per_row;
@@ -1024,6 +1037,43 @@ static inline size_t gemm_smem_bytes_bulk(int NOUT, int K, bool gated, int* nraw
         return fixed + (size_t)best_na * A_SLOT_BULK + (size_t)best_raw * slot;
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- weight images
+// The resident B operand of one GEMM: bf16, K-major rows of 128 bytes (64 channels), SWIZZLE_128B, K blocks of
+// NOUT*128 bytes -- byte for byte what the kernel prologue would build in shared memory.  One launch converts the
+// weights of every GEMM of a time step (they are re-read by all 148 CTAs of ~20 launches).
+struct WImgSpec {
+    const float* W; long w_ld, w_ks; int nrow1;
+    const float* W2; long w2_ld; int k2;
+    int NOUT, K, nout_store;
+    unsigned long long off;                  // byte offset of the image in the arena
+};
+constexpr int WIMG_MAX = 28;
+struct WImgBatch { WImgSpec s[WIMG_MAX]; int n; char* base; };
+
+__global__ void __launch_bounds__(256) wimg_kernel(const WImgBatch B) {
+    const WImgSpec& S = B.s[blockIdx.y];
+    const int K = S.K, Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
+    const int chunks_per_row = nkb * 8, total = S.NOUT * chunks_per_row, wblk_bytes = S.NOUT * 128;
+    char* img = B.base + S.off;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int n = idx / chunks_per_row, ch = idx % chunks_per_row;
+        const int kb = ch >> 3, j = ch & 7, k0 = kb * KBLK + j * 8;
+        const bool second = n >= S.nrow1;
+        const float* wrow = second ? (S.W2 + (long)(n - S.nrow1) * S.w2_ld) : (S.W + (long)n * S.w_ld);
+        const int klim = second ? (S.k2 < K ? S.k2 : K) : K;
+        const long ks = second ? 1 : S.w_ks;
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim && n < S.nout_store) ? __ldg(wrow + (long)(k0 + u) * ks) : 0.f;
+        const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        *reinterpret_cast<uint4*>(img + (size_t)kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
+    }
+}
+static inline size_t wimg_bytes(int NOUT, int K) {
+    const int Kp = (K + 15) & ~15, nkb = (Kp + KBLK - 1) / KBLK;
+    return (size_t)nkb * NOUT * 128;
 }
 
 // Host side: choose the producer mode and ring depths for a filled-in GemmParams; returns the dynamic shared memory

@@ -153,7 +153,6 @@ struct AffineOut {
 __device__ __forceinline__ void stats_finalize_last_cta(const StatSink& s, int ncontrib, unsigned ncta_total,
                                                         const AffineOut* aff) {
     __shared__ bool is_last;
-    __shared__ double red[2][32];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -163,23 +162,19 @@ __device__ __forceinline__ void stats_finalize_last_cta(const StatSink& s, int n
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // one warp per set (sets are few: <= 8 GroupNorm groups / 2 LayerNorms): lane-strided double sums in a fixed order,
+    // then a fixed shuffle tree -> deterministic, and no block-wide barrier per set
     const int nwarp = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int set = 0; set < s.nsets; ++set) {
+    for (int set = warp; set < s.nsets; set += nwarp) {
         double a = 0.0, b = 0.0;
-        for (int i = threadIdx.x; i < ncontrib; i += blockDim.x) {
+        for (int i = lane; i < ncontrib; i += 32) {
             float2 v = __ldcg(&s.partial[(size_t)set * s.stride + i]);
             a += (double)v.x; b += (double)v.y;
         }
         a = warp_sum(a); b = warp_sum(b);
-        if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double ta = 0.0, tb = 0.0;
-            for (int w = 0; w < nwarp; ++w) { ta += red[0][w]; tb += red[1][w]; }
-            s.total[set] = make_double2(ta, tb);
-        }
-        __syncthreads();
+        if (lane == 0) s.total[set] = make_double2(a, b);
     }
+    __syncthreads();
     stats_exchange(s);
     if (aff != nullptr) {
         __threadfence();

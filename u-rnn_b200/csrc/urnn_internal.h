@@ -29,6 +29,11 @@ long tc_pad_plane(long n);
 void tc_reset_direction();
 int tc_counters_begin(const urnn_cell_desc* d, void* cell_ws, size_t ws_bytes, cudaStream_t st);
 void tc_counters_end();
+// weight images of a time step (cgru_tc.cu): record the step's GEMMs, convert once, replay
+bool tc_recording();
+void tc_wimg_begin_record(void* arena, size_t cap);
+int tc_wimg_convert(cudaStream_t st);
+void tc_wimg_off();
 size_t cgru_fwd_bf16_workspace(const urnn_cell_desc* d);
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st, long x_plane = 0);
