@@ -26,11 +26,11 @@ void tc_counters_end() { g_counters_clean = false; }
 static inline long pad_plane(long n) { return (n + tc::TILE_M - 1) / tc::TILE_M * tc::TILE_M; }
 long tc_pad_plane(long n) { return pad_plane(n); }
 
-template <bool GATED, int EPI>
-static int tc_launch_t(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st) {
+template <bool GATED, int EPI, bool BULK>
+static int tc_launch_tb(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<GATED, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
+        URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<GATED, EPI, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
         attr_set = true;
     }
     // Programmatic dependent launch: the next kernel's CTAs may start their prologue (barrier init, TMEM allocation,
@@ -42,9 +42,13 @@ static int tc_launch_t(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    URNN_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_gn_kernel<GATED, EPI>, (const tc::GemmParams)P));
+    URNN_CUDA(cudaLaunchKernelEx(&cfg, tc::gemm_gn_kernel<GATED, EPI, BULK>, (const tc::GemmParams)P));
     URNN_LAUNCH_CHECK();
     return URNN_OK;
+}
+template <bool GATED, int EPI>
+static int tc_launch_t(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st) {
+    return P.bulk ? tc_launch_tb<GATED, EPI, true>(P, grid, smem, st) : tc_launch_tb<GATED, EPI, false>(P, grid, smem, st);
 }
 
 // ---- weight images of a whole time step (see tc::wimg_kernel): the step driver runs its launch sequence twice, first in

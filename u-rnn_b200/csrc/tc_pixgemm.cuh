@@ -87,6 +87,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
 }
+// 4-byte variant for fp32 rows that are only 4-byte aligned (e.g. 125 x 125 maps: planes of 15625 floats)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
 // the mbarrier receives one (pre-counted) arrival from this thread once all its earlier cp.async have landed
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -266,7 +270,9 @@ __device__ __forceinline__ void load8_quads(const float* plane_base, long q0, lo
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-template <bool GATED, int EPI>
+// BULK is a template parameter (not P.bulk) so that each instantiation carries only one producer mode: the kernel is
+// instruction-cache bound on grids with one tile per CTA (first pass through every role's code).
+template <bool GATED, int EPI, bool BULK>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     const int nkb = (Kp + KBLK - 1) / KBLK;                 // K blocks per tile
     const int last_k = Kp - (nkb - 1) * KBLK;               // valid (padded) channels in the last block
     const int wblk_bytes = NOUT * 128;
-    const bool bulk = P.bulk != 0;
+    constexpr bool bulk = BULK;
     const int nslot = bulk ? P.na : P.nstage;               // operand ring depth (8 KB slots in bulk mode, 16 KB otherwise)
     const int nu = (Kp + UNIT_K - 1) / UNIT_K;              // bulk mode: 32-channel units per tile
     const uint32_t raw_slot_bytes = GATED ? (RAW_SLOT + GRAW_SLOT) : RAW_SLOT;
@@ -305,6 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     // allow the next kernel in the stream to begin its own prologue as soon as SMs free up (PDL)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
+    if (tid < 2 * 4 * MAXG) (&red[0][0][0])[tid] = 0.f;
     if (tid == 0) {
         // one producer / converter group arrives per operand slot: 256 threads (simt) or 128 threads (bulk)
         for (int s = 0; s < nslot; ++s) { mbar_init(full0 + 8 * s, bulk ? 128 : NPROD / 2); mbar_init(empty0 + 8 * s, 1); }
@@ -743,9 +750,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                         const char* src = reinterpret_cast<const char*>(S.src[sg]) + (long)(lo - cs) * rowb + p0 * (b16 ? 2 : 4) + lane * 16;
                         uint32_t d = dst + (uint32_t)(lo - k_lo) * RAW_ROW + lane * 16;
                         const uint32_t nb = b16 ? 16u : fbytes;          // bf16 rows live in padded planes: always whole
-                        if (!b16 || lane < 16) {
+                        const bool row16 = b16 || (((reinterpret_cast<uintptr_t>(S.src[sg]) | (uintptr_t)rowb) & 15) == 0);
+                        if (row16) {
+                            if (!b16 || lane < 16) {
 #pragma unroll 4
-                            for (int c = lo; c < hi; ++c) { cp_async16(d, src, nb); src += rowb; d += RAW_ROW; }
+                                for (int c = lo; c < hi; ++c) { cp_async16(d, src, nb); src += rowb; d += RAW_ROW; }
+                            }
+                        } else {
+                            // rows are only 4-byte aligned: four 4-byte copies per lane and row (pixels lane, lane+32, ...)
+                            const char* s4 = src - lane * 12;            // = row base + lane * 4
+                            const uint32_t d4 = d - lane * 12;
+                            uint32_t v4[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) v4[q] = (lane + 32 * q < nvalid) ? 4u : 0u;
+                            for (int c = lo; c < hi; ++c) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) cp_async4(d4 + (uint32_t)(c - lo) * RAW_ROW + q * 128, s4 + (long)(c - lo) * rowb + q * 128, v4[q]);
+                            }
                         }
                         if (GATED && sg == S.gate_seg && lane < 16) {
                             const long growb = S.gate_plane * 2;
@@ -805,9 +826,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         // =========================================================================== epilogue (warps 0-7; 0-15 in bulk mode)
         regs_epilogue();
         // warp w: TMEM lanes 32*(w&3).. (pixels), 32-column groups g = (w>>2), (w>>2)+2, ... (output channels)
-        float st_s[MAXG / 2], st_ss[MAXG / 2];
-#pragma unroll
-        for (int g = 0; g < MAXG / 2; ++g) { st_s[g] = 0.f; st_ss[g] = 0.f; }
         int as = 0; uint32_t aphase = 0;
         const int ng = NOUT >> 5;
         const int lq = warp & 3, ghalf = warp >> 2, gstep = nepw >> 2;   // column groups ghalf, ghalf + gstep, ...
@@ -837,7 +855,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             tc_fence_after();
             if (warp == 0) TC_TRACE(3, (vt - (int)blockIdx.x) / (int)gridDim.x);
             const uint32_t t_addr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(as * acc_stride);
-#pragma unroll
+            // not unrolled: one copy of the group code keeps the kernel small (it is instruction-cache sensitive on grids
+            // with one tile per CTA); the per-group statistics are therefore reduced and accumulated right away
+#pragma unroll 1
             for (int gi = 0; gi < MAXG / 2; ++gi) {
                 const int g = ghalf + gstep * gi;
                 if (g < ng) {
@@ -901,7 +921,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                                 s0 += y0; s1 += y1; q0 = fmaf(y0, y0, q0); q1 = fmaf(y1, y1, q1);
                             }
                         }
-                        if (valid) { st_s[gi] += s0 + s1; st_ss[gi] += q0 + q1; }
+                        // GroupNorm partials of this CTA: lanes -> (lane quarter, group) owner warp, accumulated over tiles
+                        const float ps = warp_sum(valid ? s0 + s1 : 0.f), pq = warp_sum(valid ? q0 + q1 : 0.f);
+                        if (lane == 0) { red[0][lq][g] += ps; red[1][lq][g] += pq; }
                     } else if constexpr (EPI == EPI_LRELU) {
                         // y = LeakyReLU(acc + bias) -> NCHW (bf16 or fp32)
                         const float* bs = sbias + g * 32;
@@ -974,15 +996,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
             mbar_arrive(tempty0 + 8 * as);
             if (warp == 0) TC_TRACE(4, (vt - (int)blockIdx.x) / (int)gridDim.x);
             as ^= 1; if (as == 0) aphase ^= 1;
-        }
-        // per-CTA GroupNorm partials (fixed order: lanes -> lane quarters -> CTA)
-#pragma unroll
-        for (int gi = 0; gi < MAXG / 2; ++gi) {
-            const int g = ghalf + gstep * gi;
-            if (g < ng) {
-                float a = warp_sum(st_s[gi]), b = warp_sum(st_ss[gi]);
-                if (lane == 0) { red[0][lq][g] = a; red[1][lq][g] = b; }
-            }
         }
     }
     tc_fence_before();
@@ -1091,8 +1104,10 @@ static inline size_t plan_launch(GemmParams& P, int epi, bool allow_bulk, bool a
         const int width = P.seg.cend[i] - (i ? P.seg.cend[i - 1] : 0);
         if (width <= 0) continue;
         const size_t esz = P.seg.kind[i] ? 2 : 4;
-        bulk = bulk && (reinterpret_cast<uintptr_t>(P.seg.src[i]) & 15) == 0 && ((size_t)P.seg.plane[i] * esz) % 16 == 0;
-        bulk = bulk && (P.seg.kind[i] ? (P.seg.plane[i] >= npad) : (P.N % 4 == 0));
+        if (P.seg.kind[i])      // bf16 maps: 16-byte rows in planes padded to whole tiles
+            bulk = bulk && (reinterpret_cast<uintptr_t>(P.seg.src[i]) & 15) == 0 && ((size_t)P.seg.plane[i] * esz) % 16 == 0 && P.seg.plane[i] >= npad;
+        else                    // fp32 maps: 16-byte rows need N % 4 == 0 for the tail copy; otherwise 4-byte copies (any N)
+            bulk = bulk && (reinterpret_cast<uintptr_t>(P.seg.src[i]) & 3) == 0;
     }
     if (bulk && gated)
         bulk = (reinterpret_cast<uintptr_t>(P.seg.gate_pre) & 15) == 0 && (P.seg.gate_plane * 2) % 16 == 0 && P.seg.gate_plane >= npad;
