@@ -337,50 +337,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
-        // 16-byte chunks (8 bf16) of the swizzled image; two chunks per thread and iteration so that four 16-byte loads
-        // are in flight (the prologue is latency-bound: weights come from L2)
+        // no prepared image (stand-alone operator calls): convert the fp32 weights here.  Deliberately compact code --
+        // the time-step driver always supplies images, and kernel size matters (instruction cache).
         const int chunks_per_row = nkb * 8, total = NOUT * chunks_per_row;
-        auto wload = [&](int idx, float (&v)[8]) {
+#pragma unroll 1
+        for (int idx = tid; idx < total; idx += NTHREADS) {
             const int n = idx / chunks_per_row, ch = idx % chunks_per_row;
-            const int k0 = (ch >> 3) * KBLK + (ch & 7) * 8;
+            const int kb = ch >> 3, j = ch & 7, k0 = kb * KBLK + j * 8;
             const bool second = n >= P.nrow1;
             const float* wrow = second ? (P.W2 + (long)(n - P.nrow1) * P.w2_ld) : (P.W + (long)n * P.w_ld);
             const int klim = second ? (P.k2 < K ? P.k2 : K) : K;
             const long ks = second ? 1 : P.w_ks;
-            if (n < P.nout_store && ks == 1 && k0 + 8 <= klim && (reinterpret_cast<uintptr_t>(wrow + k0) & 15) == 0) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(wrow + k0)), b = __ldg(reinterpret_cast<const float4*>(wrow + k0) + 1);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            } else {
+            float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim && n < P.nout_store) ? __ldg(wrow + (long)(k0 + u) * ks) : 0.f;
-                if (P.bias_mma && n < P.nbias && k0 <= K + 1 && k0 + 8 > K) {      // columns K, K+1: bias = hi + lo in bf16
-                    const float b = __ldg(P.bias + n);
-                    const float hi = __bfloat162float(__float2bfloat16(b));
+            for (int u = 0; u < 8; ++u) v[u] = (k0 + u < klim && n < P.nout_store) ? __ldg(wrow + (long)(k0 + u) * ks) : 0.f;
+            if (P.bias_mma && n < P.nbias && k0 <= K + 1 && k0 + 8 > K) {      // columns K, K+1: bias = hi + lo in bf16
+                const float b = __ldg(P.bias + n);
+                const float hi = __bfloat162float(__float2bfloat16(b));
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { if (k0 + u == K) v[u] = hi; if (k0 + u == K + 1) v[u] = b - hi; }
-                }
+                for (int u = 0; u < 8; ++u) { if (k0 + u == K) v[u] = hi; if (k0 + u == K + 1) v[u] = b - hi; }
             }
-        };
-        auto wstore = [&](int idx, const float (&v)[8]) {
-            const int n = idx / chunks_per_row, ch = idx % chunks_per_row;
-            const int kb = ch >> 3, j = ch & 7;
             const uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
             *reinterpret_cast<uint4*>(sm + w_off + kb * wblk_bytes + n * 128 + ((j ^ (n & 7)) << 4)) = pk;
-        };
-        // every CTA reads the same weights at the same time: start each CTA at a different 512-byte block so that the
-        // L2 slices are not all asked for the same lines at once
-        const int nrot = total >> 5, rot = (int)((blockIdx.x * 37u) % (unsigned)nrot) << 5;
-        for (int it = tid; it < total; it += 4 * NTHREADS) {
-            float v[4][8]; int id[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int lin = it + q * NTHREADS;
-                id[q] = lin < total ? (lin + rot >= total ? lin + rot - total : lin + rot) : -1;
-                if (id[q] >= 0) wload(id[q], v[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (id[q] >= 0) wstore(id[q], v[q]);
         }
     }
     // where every reduction channel lives: plane base pointer, dtype, optional reset-gate map and folded GN affine
