@@ -315,8 +315,13 @@ def run_ours(a):
     alg_bytes = (Cx + 2 * F + F) * 4 * N
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / cell_sec / 1e9
+    # measured DRAM traffic of the same three launches: one `ncu --set full` capture (tools/prof_cell.py), committed
+    traffic, tpath = None, os.path.join(ROOT, "profiles", "r1_traffic_dec1_cell.json")
+    if os.path.exists(tpath) and (H, W) == (H_DEF, W_DEF) and a.math == "bf16":
+        with open(tpath) as f:
+            traffic = float(json.load(f)["dram_bytes_per_cell_step"])
     roofline = {"bound": "hbm", "kernel": f"decoder stage-1 Skip-ConvGRU cell step (in={Cx}, F={F}; 3 sweeps) at {H}x{W}, math={a.math}",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": cell_sec * 1e3,
                 "whole_step": {"algorithmic_bytes": (C + 2 * 188 + 160 + 1) * 4 * N,
                                "achieved_GBps": (C + 2 * 188 + 160 + 1) * 4 * N * world * a.steps / sec / 1e9 / world,

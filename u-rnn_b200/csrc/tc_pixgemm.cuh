@@ -313,10 +313,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
     // ---- one-time setup: barriers, TMEM, resident weights (fp32 -> bf16, swizzled K-major rows)
     if (tid < 2 * 4 * MAXG) (&red[0][0][0])[tid] = 0.f;
     if (tid == 0) {
-        // one producer / converter group arrives per operand slot: 256 threads (simt) or 128 threads (bulk)
-        for (int s = 0; s < nslot; ++s) { mbar_init(full0 + 8 * s, bulk ? 128 : NPROD / 2); mbar_init(empty0 + 8 * s, 1); }
-        if (bulk) for (int s = 0; s < P.nraw; ++s) { mbar_init(rfull0 + 8 * s, 32); mbar_init(rempty0 + 8 * s, 128); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, bulk ? NEPI_BULK : NEPI); }
+        // Arrivals are per WARP (lane 0 after __syncwarp), not per thread: every arrive is a SYNCS event that wakes the
+        // warps parked in NANOSLEEP.SYNCS, and 128-512 arrivals per unit kept them polling (31 % of executed instructions).
+        // One producer / converter group per operand slot: 8 warps (simt) or 4 warps (bulk).
+        for (int s = 0; s < nslot; ++s) { mbar_init(full0 + 8 * s, bulk ? 4 : NPROD / 64); mbar_init(empty0 + 8 * s, 1); }
+        if (bulk) for (int s = 0; s < P.nraw; ++s) { mbar_init(rfull0 + 8 * s, 32); mbar_init(rempty0 + 8 * s, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, (bulk ? NEPI_BULK : NEPI) / 32); }
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
@@ -529,7 +531,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 *reinterpret_cast<uint4*>(st + soff0 + c * 2048) = pk;
             }
             fence_proxy_async();                             // generic-proxy stores -> visible to tcgen05.mma
-            mbar_arrive(full0 + 8 * stage);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * stage);
             if (warp == NEPI / 32 && kb == nkb - 1) { TC_TRACE(1, trace_i); ++trace_i; }
         };
 
@@ -663,13 +666,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                         pk[c] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);   // bf16 ones
                     }
                 }
-                mbar_arrive(rempty0 + 8 * rs);               // staging slot consumed (values are in registers)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rempty0 + 8 * rs); // staging slot consumed (values are in registers)
                 mbar_wait<64>(empty0 + 8 * as, aph ^ 1);
                 uint8_t* st = sm + a_off + as * A_SLOT_BULK;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(st + so0 + c * 1024) = pk[c];
                 fence_proxy_async();                         // generic-proxy stores -> visible to tcgen05.mma
-                mbar_arrive(full0 + 8 * as);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * as);
                 if (warp == NEPI_BULK / 32 && kb == nu - 1) { TC_TRACE(1, trace_i); ++trace_i; }
             }
         }
@@ -971,7 +976,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_gn_kernel(const GemmParams P
                 }
             }
             tc_fence_before();
-            mbar_arrive(tempty0 + 8 * as);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * as);
             if (warp == 0) TC_TRACE(4, (vt - (int)blockIdx.x) / (int)gridDim.x);
             as ^= 1; if (as == 0) aphase ^= 1;
         }
