@@ -75,7 +75,7 @@ int urnn_cgru_fwd(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     switch (d->math) {
         case URNN_MATH_FP32: return cgru_fwd_fp32(d, p, x, e, h, h_out, ws, ws_bytes, st);
 #ifndef URNN_NO_TC
-        case URNN_MATH_BF16: return cgru_fwd_bf16(d, p, x, 0, e, h, h_out, ws, ws_bytes, st);
+        case URNN_MATH_BF16: return cgru_fwd_bf16_standalone(d, p, x, 0, e, h, h_out, ws, ws_bytes, st);
 #endif
         default: set_error("cgru_fwd: math mode %d not built", d->math); return URNN_E_UNSUPPORTED;
     }

@@ -207,8 +207,9 @@ cgru_blend_bf16_kernel(const __nv_bfloat16* __restrict__ G, const __nv_bfloat16*
 
 struct CellWsBf16 {
     unsigned* counter; double2 *total1, *total2; float *scale1, *shift1, *scale2, *shift2;
-    float2 *partial1, *partial2; __nv_bfloat16 *GP, *C; int gx;
+    float2 *partial1, *partial2; __nv_bfloat16 *GP, *C; int gx; char* wimg;
 };
+constexpr size_t CELL_WIMG_BYTES = 256 << 10;      // weight images of a stand-alone cell call (sweep A + sweep B)
 
 static size_t cell_ws_bf16(const urnn_cell_desc* d, void* ws, size_t ws_bytes, CellWsBf16* out) {
     const long N = (long)d->H * d->W;
@@ -225,6 +226,7 @@ static size_t cell_ws_bf16(const urnn_cell_desc* d, void* ws, size_t ws_bytes, C
     const size_t Np = (size_t)pad_plane(N);            // bf16 planes are padded to whole 128-pixel tiles (bulk copies)
     w.GP = a.take<__nv_bfloat16>((size_t)3 * F * Np);
     w.C = a.take<__nv_bfloat16>((size_t)F * Np);
+    w.wimg = a.take<char>(CELL_WIMG_BYTES);
     if (out) *out = w;
     return align_up(a.off, 256);
 }
@@ -330,6 +332,24 @@ int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void
     }
     URNN_LAUNCH_CHECK();
     return URNN_OK;
+}
+
+// Stand-alone cell call (urnn_cgru_fwd): same record -> convert -> replay of the weight images as the step driver.
+int cgru_fwd_bf16_standalone(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
+                             const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (d->ksize != 1 || g_wimg.mode != WIMG_OFF) return cgru_fwd_bf16(d, p, x, xkind, e, h, h_out, ws, ws_bytes, st);
+    CellWsBf16 w;
+    size_t need = cell_ws_bf16(d, ws, ws_bytes, &w);
+    if (need > ws_bytes) { set_error("cgru_fwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
+    URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
+    struct Guard { ~Guard() { g_counters_clean = false; tc_wimg_off(); } } guard;
+    g_counters_clean = true;
+    tc_wimg_begin_record(w.wimg, CELL_WIMG_BYTES);
+    tc_reset_direction();
+    URNN_TRY(cgru_fwd_bf16(d, p, x, xkind, e, h, h_out, ws, ws_bytes, st));
+    URNN_TRY(tc_wimg_convert(st));
+    tc_reset_direction();
+    return cgru_fwd_bf16(d, p, x, xkind, e, h, h_out, ws, ws_bytes, st);
 }
 
 }  // namespace urnn

@@ -37,6 +37,8 @@ void tc_wimg_off();
 size_t cgru_fwd_bf16_workspace(const urnn_cell_desc* d);
 int cgru_fwd_bf16(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
                   const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st, long x_plane = 0);
+int cgru_fwd_bf16_standalone(const urnn_cell_desc* d, const urnn_cell_params* p, const void* x, int xkind, const float* e,
+                             const float* h, float* h_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope, const void* x, int xkind,
                          const float* w, long w_ld, const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st,
                          long x_plane = 0, long y_plane = 0);
