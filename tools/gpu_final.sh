@@ -10,5 +10,5 @@ timeout 300 python bench.py --math fp32 --steps 30 --no-cpu-baseline --watchdog 
 timeout 300 python bench.py --impl reference --steps 4 --warmup 1 > $OUT/bench_ref.json 2>/dev/null; echo "ref rc=$?"; cat $OUT/bench_ref.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 140 --csv --log-file $OUT/launches.csv python bench.py --value-only --steps 2 --warmup 2 > $OUT/ncu_bench.log 2>&1
 python tools/launch_summary.py $OUT/launches.csv > $OUT/launches.txt 2>&1; tail -3 $OUT/launches.txt
-timeout 300 ncu --set full --import-source on --clock-control none -s 6 -c 3 -f -o $OUT/cell python tools/prof_cell.py > $OUT/ncu_cell.log 2>&1; echo "ncu cell rc=$?"
+timeout 300 ncu --set full --import-source on --clock-control none -k "regex:gemm_gn_kernel|cgru_blend" -s 6 -c 3 -f -o $OUT/cell python tools/prof_cell.py > $OUT/ncu_cell.log 2>&1; echo "ncu cell rc=$?"
 ncu -i $OUT/cell.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_traffic.py > $OUT/traffic.json; cat $OUT/traffic.json | head -40

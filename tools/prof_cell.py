@@ -1,7 +1,7 @@
 """The bench's roofline kernel in isolation, for ncu: the full-resolution decoder Skip-ConvGRU cell step (3 launches)
 at 500 x 500, run 3 times.  Usage under ncu:
-  ncu --set full --import-source on --clock-control none -s 6 -c 3 -f -o gpurun_out/cell python tools/prof_cell.py
-(launches 0-5 warm up; 6-8 are sweep A, sweep B and the blend of the third step)."""
+  ncu --set full --import-source on --clock-control none -k "regex:gemm_gn_kernel|cgru_blend" -s 6 -c 3 -f -o gpurun_out/cell python tools/prof_cell.py
+(of the matching kernels, launches 0-5 warm up; 6-8 are sweep A, sweep B and the blend of the third step)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "u-rnn_b200")]

@@ -73,9 +73,10 @@ def run(nraw, na, nu, ntile, seed, NG=2, NL=2):
         steps+=1
         if steps>200000: return "DEADLOCK/livelock"
     return "ok"
-bad=0
-for nraw,na,nu,ntile in itertools.product((2,4,6),range(2,5),range(1,11),range(1,5)):
-    for seed in range(6):
-        r=run(nraw,na,nu,ntile,seed)
-        if r!="ok": print(nraw,na,nu,ntile,seed,r); bad+=1
-print("bad",bad)
+if __name__ == '__main__':
+    bad=0
+    for nraw,na,nu,ntile in itertools.product((2,4,6),range(2,5),range(1,11),range(1,5)):
+        for seed in range(6):
+            r=run(nraw,na,nu,ntile,seed)
+            if r!="ok": print(nraw,na,nu,ntile,seed,r); bad+=1
+    print("bad",bad)

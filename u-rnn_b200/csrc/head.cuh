@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(128) head_kernel(HeadDev hd, const float* __re
     __shared__ __align__(16) float w[5][256];
     __shared__ float pw[2][16];
     __shared__ float red[2][2][4];
-    for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) w[i / 256][i % 256] = __ldg(hd.p.conv_w[i / 256] + (i % 256));
+    // only the mat-vecs this level evaluates: stem | + cls_convs.0, reg_convs.0 (indices 1, 3) | all five
+    constexpr int NEED = (LEVEL == 0) ? 0x01 : (LEVEL == 1 ? 0x0B : 0x1F);
+    for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x)
+        if ((NEED >> (i / 256)) & 1) w[i / 256][i % 256] = __ldg(hd.p.conv_w[i / 256] + (i % 256));
     if (threadIdx.x < 16) {
         pw[0][threadIdx.x] = __ldg(hd.p.cls_pred_w + threadIdx.x);
         pw[1][threadIdx.x] = __ldg(hd.p.reg_pred_w + threadIdx.x);
