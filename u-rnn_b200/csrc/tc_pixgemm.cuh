@@ -1,30 +1,29 @@
 // tc_pixgemm.cuh -- tcgen05 "pixel GEMM" for sm_100a:  D[128 pixels x NOUT] = X^T[128 x K] * W^T[K x NOUT]
 // with bf16 operands (rounded on the fly from the fp32 / bf16 NCHW maps) and fp32 accumulation in tensor memory.
 //
-// One persistent CTA per SM, 25 warps, warp-specialised:
-//   warps 0-7   epilogue : tcgen05.ld the accumulator (TMEM lane = pixel, column = output channel); fused epilogue
-//                          (bias, optional addend map, GroupNorm statistics, bf16 NCHW store)
-//   warps 8-23  producers (two independent groups of 8 warps, alternating ring slots): build the A tile.  It is stored MN-major (pixel-contiguous) exactly like the NCHW source,
-//                          so a thread moves 8 consecutive pixels of one channel (two 16-byte global loads -> 8 bf16
-//                          -> one 16-byte shared store) and a half-warp covers the 512 contiguous bytes a channel
-//                          contributes to the tile.  The channel axis is a virtual concatenation of up to three maps;
-//                          one segment can be multiplied by the reset gate sigmoid(GN(G_r)) on the way in.
-//   warp  24    MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=NOUT, K=16 per instruction
-// Pipelines: K-block ring in shared memory (full/empty mbarriers, producer -> MMA) and a double-buffered
-// accumulator in TMEM (tmem_full/tmem_empty mbarriers, MMA -> epilogue), so loads, MMAs and epilogues of
-// successive 128-pixel tiles overlap; producers additionally keep the loads of the next ring slot in flight
-// while converting the current one.  Weights are converted once per CTA and stay resident in shared memory.
+// One persistent CTA per SM, 28 warps (7 warpgroups), warp-specialised.  Activations must be rounded fp32 -> bf16 (and,
+// for the candidate GEMM, multiplied by the reset gate) before the tensor core sees them, so a SIMT stage always sits
+// between HBM and the MMA operand.  The operand is stored MN-major (pixel-contiguous, SWIZZLE_128B) exactly like the
+// NCHW source: no transposition.  The channel axis is a virtual concatenation of up to three maps.
 //
-// Activations must be rounded fp32 -> bf16 (and, for the candidate GEMM, multiplied by the reset gate) before the
-// tensor core sees them, so a SIMT stage always sits between HBM and the MMA operand.  Two producer modes:
-//   bulk (default whenever every source plane is 16-byte aligned): warps 25-26 stream the raw fp32 / bf16 channel rows
-//        of a unit (32 channels x 128 pixels) into a staging ring with 16-byte cp.async (LDGSTS) copies whose
-//        completion is collected by an mbarrier -- up to 6 units (96 KB) in flight per SM, no registers held -- and
-//        warps 8-23 only convert staging -> swizzled bf16 operand (shared -> shared).  Their fence.proxy.async
-//        (MEMBAR.ALL.CTA) then has no global loads to wait for.  (1-D TMA bulk copies were tried first: a 512-byte
-//        row per UBLKCP is too small, 11 GB/s per SM.)
-//   simt (fallback for unaligned planes, e.g. 125 x 125 maps, and the 2x2 pooling gather): warps 8-23 load from
-//        global memory themselves (64-channel units).
+// BULK = true (default; every fp32 map, bf16 maps with planes padded to whole tiles):
+//   warps 25-26 loaders   : stream the raw channel rows of a unit (32 channels x 128 pixels) into a staging ring with
+//                           16-byte cp.async (8-byte for the 2x2 pooling gather, 4-byte for planes that are only 4-byte
+//                           aligned); completion is collected per unit by an mbarrier, no registers are held, 4-6 units
+//                           (64-96 KB) are in flight per SM.  (1-D TMA bulk copies were tried first: a 512-byte row per
+//                           UBLKCP is too small, 11 GB/s per SM.)
+//   warps 16-23 converters: two groups of 4 warps, alternating units: staging -> (reset gate) -> bf16 -> operand slot
+//   warp  24    MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128, N=NOUT, K=16 per instruction, tcgen05.commit
+//   warps 0-15  epilogue  : tcgen05.ld (TMEM lane = pixel, column = output channel); bias, addend map, GroupNorm
+//                           statistics, LeakyReLU / pooling / 2x2 scatter; bf16 rows leave through a per-warp transpose tile
+//                           as 16-byte pieces
+// BULK = false (bf16 maps without padded planes; URNN_BULK=0): warps 8-23 are SIMT producers that load from global
+//   memory themselves (64-channel units, two groups of 8 warps), warps 0-7 the epilogue.
+//
+// Pipelines: staging ring (raw_full / raw_empty), operand ring (full / empty), double-buffered accumulator in TMEM
+// (tmem_full / tmem_empty).  Waits park in hardware (mbarrier.try_wait with a suspend-time hint), arrivals are
+// warp-elected, register budgets are re-partitioned per role with setmaxnreg.  Weights stay resident in shared memory;
+// the time-step driver hands every GEMM a pre-converted bf16 image (wimg_kernel), stand-alone calls convert in the prologue.
 #pragma once
 #include <cuda_bf16.h>
 #include "urnn_common.cuh"
