@@ -173,7 +173,7 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps} ED steps at {H}x{W} after {warmup} warm-up, torch {torch.__version__} CPU"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -246,11 +246,11 @@ def run_ours(a):
 
     if a.value_only:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                               "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                               "dtype": {"fp32": "f32", "bf16": "bf16"}[a.math], "data": "synthetic",
                               "config": {"workload": f"{world * H}x{W}, C_in={C}, ED step forward, value only", "math": a.math},
-                              "gpu_launches": int(launches), "clocks": clk.summary()}))
+                              "gpu_launches": int(launches), "clocks": clk.summary()})
         if dist is not None:
             from urnn_b200 import dist as ud
             ud.shutdown_spatial_sharding()
@@ -350,18 +350,47 @@ def run_ours(a):
                               "d2h_bytes_per_step": N * 4, "ms_per_step": sec_ev / a.steps * 1e3,
                               "path": "urnn_ed_event_host: raw maps + scalar rainfall from the host once, per-step input assembly fused into the stage-1 stem"},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         from urnn_b200 import dist as ud
         ud.shutdown_spatial_sharding()
         dist.destroy_process_group()
 
 
+class StdoutToStderr:
+    """stdout must carry exactly one JSON line, but NCCL prints its banner ("NCCL version ...") to fd 1 when the box
+    exports NCCL_DEBUG: while the benchmark runs, fd 1 points at stderr; `restore()` is called right before the line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
+
+
+_REDIRECT = None
+
+
+def emit(line):
+    if _REDIRECT is not None:
+        _REDIRECT.restore()
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    global _REDIRECT
     a = parse()
     # a wedged GPU must not hang the caller: dump the Python stack and exit instead
     import faulthandler
     faulthandler.dump_traceback_later(a.watchdog, exit=True)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        _REDIRECT = StdoutToStderr()
     if a.impl == "reference":
         run_reference_arm(a)
     else:
