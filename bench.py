@@ -342,6 +342,9 @@ def run_ours(a):
                 "config": {"workload": f"location1 full-res {grid}, C_in={C}, ED step forward (6 ConvGRU cells + stems + head)",
                            "l2": "per-step working set ~600 MB (states in+out, inputs, LN affine) > 126 MB L2; inputs cycle through a ring of 8",
                            "weights": "random init, torch.manual_seed(0)", "math": a.math,
+                           "parity": "per-step parity tests in tests/ (fp32: 1e-5 vs the reference; bf16: the mode's model); bf16 vs fp32 drift over T=180 "
+                                     "with random-init weights: profiles/r1_config3_drift.json (R2 0.973)" if a.math == "bf16" else "fp32: atol 1e-5 / rtol 1e-4 vs the reference",
+
                            "sharding": "row bands, in-kernel NVLink statistic all-reduce" if world > 1 else "none",
                            "e2e_path": f"urnn_ed_sequence_host (C ABI, host buffers), {chunk}-step calls"},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": C * N * 4, "d2h_bytes_per_step": N * 4,
