@@ -1,0 +1,541 @@
+// gemm_v2.cuh -- tcgen05 "pixel GEMM" for sm_100a, second generation:  D[128 pixels x N] = X^T[128 x K] * W^T[K x N]
+//
+// Precision: every operand is a bf16 hi + lo pair (v = hi + lo, 16-17 significant bits) and every K=16 step issues
+// three MMAs  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  into an fp32 accumulator in tensor memory.  (Measured on the reference's
+// recurrence, tools/precision_sweep.py: single-pass bf16/tf32 operands or bf16 intermediate maps leave the config-3
+// tolerance at T=180; >= 16-bit operands on BOTH sides with fp32 intermediates stay inside it.)
+//
+// Data path: activations live in HBM as "split maps"  [2 (hi|lo)][C][Ntot] bf16, pixel-contiguous.  A TMA tensor load
+// (box 64 pixels x unit channels x {hi,lo}, SWIZZLE_128B) lands them directly in the canonical MN-major UMMA layout: no
+// SIMT stage between HBM and the tensor core.  The only SIMT-produced operand is the reset-gated state r*h of the
+// candidate GEMM (K = F channels), written by four gate warps.  Weights are resident in shared memory as a hi and a lo
+// image (K-major SWIZZLE_128B), prepared once per sequence.
+//
+// One persistent CTA per SM:  warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM owner, warps 4-11 epilogue
+// (tcgen05.ld: lane = pixel, column = output channel), warps 12-15 gate warps (gated launches only).
+// Pipelines: operand ring (full/empty), gated-operand buffers (gfull/gempty), accumulator stages (tfull/tempty).
+#pragma once
+#include <cuda.h>
+#include "ptx_sm100.cuh"
+#include "urnn_common.cuh"
+
+namespace urnn {
+namespace v2 {
+
+using namespace ptx;
+
+constexpr int TILE_M = 128;
+constexpr int SLOT_BYTES = 16384;         // one ring slot: 32 channels x 128 pixels x {hi,lo} bf16
+constexpr int MAX_STEPS = 16;
+constexpr int MAXG = 8;                   // 32-column groups per accumulator (N <= 256)
+constexpr int NWARP_EPI = 8;
+constexpr int EPI_WARP0 = 4, GATE_WARP0 = 12;
+constexpr int NTHREADS_PLAIN = 32 * GATE_WARP0, NTHREADS_GATED = 32 * (GATE_WARP0 + 4);
+constexpr size_t SMEM_MAX = 231424;       // 227 KB opt-in limit minus 1 KB for static shared memory
+
+enum { EPI_STATS_F32 = 0, EPI_LRELU_SPLIT = 1, EPI_LRELU_F32 = 2 };
+enum { ACC_SINGLE = 0, ACC_POOL = 1, ACC_DECONV = 2 };
+
+// ---- normalisation statistics, mean-shifted: every epilogue warp keeps (n, S1 = sum(x-K), S2 = sum((x-K)^2), K) per group
+// with its own pilot K (the first value it sees), the last CTA converts the partials to (n, mean, M2) in double and merges
+// them with Chan's formula in a fixed order: no E[x^2]-E[x]^2 cancellation however large |mean|/sigma is.
+struct StatSink2 {
+    float4*   partial;   // [nsets][stride]
+    double*   total;     // [nsets][4] = (mean, M2, n, -)
+    unsigned* counter;
+    int       nsets;
+    int       stride;    // >= NWARP_EPI * CTAs
+    CommDev   comm;
+};
+
+__device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, double nb, double meanb, double m2b) {
+    if (nb <= 0.0) return;
+    if (n <= 0.0) { n = nb; mean = meanb; m2 = m2b; return; }
+    const double nn = n + nb, d = meanb - mean;
+    mean += d * (nb / nn);
+    m2 += m2b + d * d * (n * nb / nn);
+    n = nn;
+}
+
+// One-shot all-reduce of the (mean, M2, n) triples over NVLink peer memory (same protocol as stats_exchange).
+__device__ __forceinline__ void stats2_exchange(const StatSink2& s) {
+    const CommDev& c = s.comm;
+    if (c.world <= 1) return;
+    __shared__ unsigned sh_seq;
+    if (threadIdx.x == 0) sh_seq = *c.seq;
+    __syncthreads();
+    const unsigned seq = sh_seq, ring = seq % COMM_RING, epoch = seq / COMM_RING + 1;
+    const int slot0 = (int)(ring * c.world + c.rank) * COMM_MAX_SETS;
+    for (int i = threadIdx.x; i < c.world * s.nsets; i += blockDim.x) {
+        const int peer = i / s.nsets, set = i % s.nsets;
+        c.slots[peer][slot0 + set] = make_double4(s.total[4 * set], s.total[4 * set + 1], s.total[4 * set + 2], 0.0);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + ring * c.world + c.rank, epoch);
+    if (threadIdx.x < c.world) {
+        const unsigned* f = c.flags[c.rank] + ring * c.world + threadIdx.x;
+        while (ld_acquire_sys(f) != epoch) { __nanosleep(64); }
+    }
+    __syncthreads();
+    if (threadIdx.x < s.nsets) {
+        double n = 0.0, mean = 0.0, m2 = 0.0;
+        for (int r = 0; r < c.world; ++r) {
+            const volatile double4* src = c.slots[c.rank] + (int)(ring * c.world + r) * COMM_MAX_SETS + threadIdx.x;
+            chan_merge(n, mean, m2, src->z, src->x, src->y);
+        }
+        s.total[4 * threadIdx.x] = mean; s.total[4 * threadIdx.x + 1] = m2; s.total[4 * threadIdx.x + 2] = n;
+    }
+    if (threadIdx.x == 0) *c.seq = seq + 1;
+    __syncthreads();
+}
+
+// Called by ALL threads of the CTA after its partials are written.  The last CTA merges, exchanges, folds the affine.
+__device__ __forceinline__ void stats2_finalize_last_cta(const StatSink2& s, int ncontrib, unsigned ncta_total, const AffineOut* aff) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(s.counter, 1u);
+        is_last = (t == ncta_total - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int nwarp = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int set = warp; set < s.nsets; set += nwarp) {
+        double n = 0.0, mean = 0.0, m2 = 0.0;
+        for (int i = lane; i < ncontrib; i += 32) {
+            const float4 v = __ldcg(&s.partial[(size_t)set * s.stride + i]);
+            if (v.x > 0.f) {
+                const double nb = (double)v.x, s1 = (double)v.y, s2 = (double)v.z;
+                chan_merge(n, mean, m2, nb, (double)v.w + s1 / nb, s2 - s1 * s1 / nb);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {          // fixed tree: deterministic
+            const double nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                         qb = __shfl_xor_sync(0xffffffffu, m2, o);
+            // both partners must compute the same result: merge in (lower lane, higher lane) order
+            if (lane & o) { double n2 = nb, me2 = mb, q2 = qb; chan_merge(n2, me2, q2, n, mean, m2); n = n2; mean = me2; m2 = q2; }
+            else chan_merge(n, mean, m2, nb, mb, qb);
+        }
+        if (lane == 0) { s.total[4 * set] = mean; s.total[4 * set + 1] = m2; s.total[4 * set + 2] = n; }
+    }
+    __syncthreads();
+    stats2_exchange(s);
+    if (aff != nullptr && aff->scale != nullptr) {
+        __threadfence();
+        for (int c = threadIdx.x; c < aff->channels; c += blockDim.x) {
+            const int set = c / aff->ch_per_set;
+            const double mean = s.total[4 * set], n = s.total[4 * set + 2];
+            double var = n > 0.0 ? s.total[4 * set + 1] / n : 0.0;
+            if (var < 0.0) var = 0.0;
+            const double rstd = 1.0 / sqrt(var + (double)aff->eps);
+            const double sc = (double)aff->gamma[c] * rstd;
+            aff->scale[c] = (float)sc;
+            aff->shift[c] = (float)((double)aff->beta[c] - mean * sc);
+        }
+    }
+    if (threadIdx.x == 0) *s.counter = 0u;
+}
+
+// ---- launch description
+struct Step {                 // one TMA-loaded operand unit of a tile
+    int map;                  // tensor map index (0..2)
+    int c0;                   // first channel inside that map
+    int unit_ch;              // 16 or 32 channels
+    int kglob;                // position in the weight image's K axis
+    int acc;                  // accumulator (ACC_POOL: one per 2x2 phase)
+    int pad;
+    long long pix_off;        // added to the tile's first pixel (phase block offsets)
+};
+
+struct GemmParams {
+    Step steps[MAX_STEPS]; int nsteps;
+    int nacc, acc_mode;
+    // reset-gated operand segment (candidate GEMM): r*h with r = sigmoid(gate_pre*scale + shift), produced by the gate warps
+    int gate_ch;                                   // 0: none, else F (multiple of 32)
+    int gate_k0;                                   // position of the gated channels in the weight image's K axis
+    const __nv_bfloat16* gate_h; long long gate_h_plane, gate_h_lo;    // split map of h: hi planes, lo planes gate_h_lo elements further
+    const float* gate_pre; long long gate_pre_plane;                   // fp32 pre-GroupNorm reset-gate map [F][plane]
+    const float* gate_scale; const float* gate_shift;                  // folded GroupNorm affine of those F channels
+    int gdepth;                                    // gated-operand buffers (1 or 2)
+    // weights: resident image, hi then lo, each nkb blocks of (nrows x 128 B) (64 channels, K-major, SWIZZLE_128B)
+    const void* wimg; int nkb, nrows;
+    int N;                                         // columns per accumulator (multiple of 16, <= 256)
+    int nmma;                                      // 3: hi/lo split product; 1: single bf16 pass
+    // pixels: tiles cover [0, ntot); pixel p is real iff (p % blk_stride) < blk_valid
+    long long ntot, blk_stride, blk_valid;
+    // epilogue
+    int epi; float slope;
+    const float* bias; int nbias, bias_mod;        // bias[col % bias_mod] for col < nbias
+    float* out_f32; long long out_plane;           // fp32 planes out_f32[col*out_plane + p]
+    int store_c0, store_c1;                        // EPI_STATS_F32: columns [store_c0, store_c1) are stored
+    __nv_bfloat16* out_hi; long long out_lo;       // split map destination: hi planes, lo planes out_lo elements further
+    long long out_acc_stride;                      // ACC_DECONV: pixel offset between the destination blocks of the accumulators
+    int nstat; StatSink2 sink; AffineOut aff;      // leading 32-column groups with GroupNorm statistics
+    int nslots, tmem_cols, acc_stages, acc_stride; // ring depth; TMEM allocation; stages and column stride between accumulators
+};
+
+struct SmemPlan { uint32_t w_off, ring_off, gbuf_off, bias_off, gaff_off, bar_off, red_off, total; };
+
+__host__ __device__ inline SmemPlan smem_plan(int nkb, int nrows, int nslots, int gate_ch, int gdepth, int ncols_total) {
+    SmemPlan s;
+    uint32_t o = 0;
+    s.w_off = o; o += 2u * nkb * nrows * 128u;
+    s.ring_off = o; o += (uint32_t)nslots * SLOT_BYTES;
+    s.gbuf_off = o; o += (uint32_t)gdepth * (gate_ch / 32) * SLOT_BYTES;
+    s.bias_off = o; o += ((uint32_t)ncols_total * 4u + 127u) & ~127u;
+    s.gaff_off = o; o += ((uint32_t)gate_ch * 8u + 127u) & ~127u;
+    s.bar_off = o; o += 512;
+    s.red_off = o; o += NWARP_EPI * MAXG * 16;
+    s.total = o + 1024;      // alignment slack
+    return s;
+}
+
+template <bool GATED>
+__global__ void __launch_bounds__(GATED ? NTHREADS_GATED : NTHREADS_PLAIN, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+            const __grid_constant__ CUtensorMap map2, const GemmParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthreads = GATED ? NTHREADS_GATED : NTHREADS_PLAIN;
+    const int ncols_total = P.acc_mode == ACC_DECONV ? P.nacc * P.N : P.N;
+    const SmemPlan L = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total);
+    // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | gfull[2] | gempty[2] | tmem slot
+    const uint32_t full0 = base + L.bar_off, empty0 = full0 + 64, tfull0 = empty0 + 64, tempty0 = tfull0 + 16;
+    const uint32_t gfull0 = tempty0 + 16, gempty0 = gfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bar_off + 256);
+    float* sbias = reinterpret_cast<float*>(sm + L.bias_off);
+    float* sgaff = reinterpret_cast<float*>(sm + L.gaff_off);
+    float4* red = reinterpret_cast<float4*>(sm + L.red_off);     // [NWARP_EPI][MAXG] = (n, S1, S2, K)
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // ---- one-time setup (reads only parameters and the constant weight image)
+    if (tid == 0) {
+        for (int s = 0; s < P.nslots; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NWARP_EPI);
+            mbar_init(gfull0 + 8 * a, 4); mbar_init(gempty0 + 8 * a, 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&map0); tma_prefetch_desc(&map1); tma_prefetch_desc(&map2); }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
+    for (int i = tid; i < NWARP_EPI * MAXG; i += nthreads) red[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < ncols_total; i += nthreads) sbias[i] = (P.bias != nullptr && i < P.nbias) ? __ldg(P.bias + (i % P.bias_mod)) : 0.f;
+    {
+        const int nvec = 2 * P.nkb * P.nrows * 8;            // 16-byte pieces of the weight image
+        const char* src = reinterpret_cast<const char*>(P.wimg);
+        const int rot = (int)((blockIdx.x * 37u) % (unsigned)(nvec >> 5)) << 5;   // CTAs start at different L2 lines
+        for (int i = tid; i < nvec; i += nthreads) {
+            const int j = i + rot >= nvec ? i + rot - nvec : i + rot;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + L.w_off + (uint32_t)j * 16u), "l"(src + (size_t)j * 16u));
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // from here on the previous kernel's outputs are consumed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if constexpr (GATED) {
+        for (int i = tid; i < P.gate_ch; i += nthreads) { sgaff[2 * i] = __ldg(P.gate_scale + i); sgaff[2 * i + 1] = __ldg(P.gate_shift + i); }
+        __syncthreads();
+    }
+    const long long ntiles = P.ntot / TILE_M;
+    const uint32_t wlo = (uint32_t)P.nkb * P.nrows * 128u;   // lo image offset
+
+    if (warp == 0) {
+        // =========================================================================== TMA producer
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const long long p0 = tile * TILE_M;
+                for (int s = 0; s < P.nsteps; ++s) {
+                    const Step& st = P.steps[s];
+                    mbar_wait(empty0 + 8 * slot, ph ^ 1);
+                    const uint32_t dst = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
+                    const uint32_t bar = full0 + 8 * slot;
+                    const uint32_t half_bytes = (uint32_t)st.unit_ch * 128u * (P.nmma == 3 ? 2u : 1u);
+                    mbar_arrive_expect_tx(bar, 2u * half_bytes);
+                    const void* m = st.map == 0 ? (const void*)&map0 : (st.map == 1 ? (const void*)&map1 : (const void*)&map2);
+                    const int px = (int)(p0 + st.pix_off);
+                    tma_load_3d(dst, m, bar, px, st.c0, 0, L2_EVICT_NORMAL);
+                    tma_load_3d(dst + half_bytes, m, bar, px + 64, st.c0, 0, L2_EVICT_NORMAL);
+                    if (++slot == P.nslots) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================================== MMA issuer
+        const uint32_t idesc = instr_desc_bf16(P.N);
+        int slot = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0; int gd = 0; uint32_t gph = 0;
+        const uint32_t hl = P.nmma == 3 ? 2u : 1u;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(tempty0 + 8 * as, aph ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + (uint32_t)(as * P.nacc * P.acc_stride);
+            for (int s = 0; s < P.nsteps; ++s) {
+                const Step& st = P.steps[s];
+                mbar_wait(full0 + 8 * slot, ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_base = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
+                    const uint32_t lbo = (uint32_t)st.unit_ch * 128u * hl, lo_off = (uint32_t)st.unit_ch * 128u;
+                    for (int j = 0; j < (st.unit_ch >> 4); ++j) {
+                        const int k = st.kglob + 16 * j;
+                        const uint32_t b_base = base + L.w_off + (uint32_t)(k >> 6) * P.nrows * 128u + (uint32_t)((k & 63) >> 4) * 32u;
+                        const uint64_t a_hi = smem_desc_mn_sw128(a_base + j * 2048, lbo);
+                        const uint64_t a_lo = smem_desc_mn_sw128(a_base + lo_off + j * 2048, lbo);
+                        const int na = P.acc_mode == ACC_DECONV ? P.nacc : 1;
+                        for (int a = 0; a < na; ++a) {
+                            const int acc = P.acc_mode == ACC_DECONV ? a : st.acc;
+                            const uint32_t d = d0 + (uint32_t)(acc * P.acc_stride);
+                            const uint32_t b = b_base + (uint32_t)(a * P.N) * 128u;
+                            const uint32_t first = (P.acc_mode == ACC_POOL ? k : (s | j)) == 0 ? 0u : 1u;
+                            umma_f16(d, a_hi, smem_desc_sw128(b), idesc, first);
+                            if (P.nmma == 3) {
+                                umma_f16(d, a_lo, smem_desc_sw128(b), idesc, 1u);
+                                umma_f16(d, a_hi, smem_desc_sw128(b + wlo), idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit(empty0 + 8 * slot);
+                }
+                __syncwarp();
+                if (++slot == P.nslots) { slot = 0; ph ^= 1; }
+            }
+            if constexpr (GATED) {
+                mbar_wait(gfull0 + 8 * gd, gph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t g_base = base + L.gbuf_off + (uint32_t)gd * (P.gate_ch / 32) * SLOT_BYTES;
+                    for (int u = 0; u < P.gate_ch / 32; ++u)
+                        for (int j = 0; j < 2; ++j) {
+                            const int k = P.gate_k0 + 32 * u + 16 * j;
+                            const uint32_t b = base + L.w_off + (uint32_t)(k >> 6) * P.nrows * 128u + (uint32_t)((k & 63) >> 4) * 32u;
+                            const uint32_t a = g_base + (uint32_t)u * SLOT_BYTES + j * 2048;
+                            const uint64_t a_hi = smem_desc_mn_sw128(a, 8192), a_lo = smem_desc_mn_sw128(a + 4096, 8192);
+                            const uint32_t first = (P.nsteps == 0 && (u | j) == 0) ? 0u : 1u;
+                            umma_f16(d0, a_hi, smem_desc_sw128(b), idesc, first);
+                            if (P.nmma == 3) {
+                                umma_f16(d0, a_lo, smem_desc_sw128(b), idesc, 1u);
+                                umma_f16(d0, a_hi, smem_desc_sw128(b + wlo), idesc, 1u);
+                            }
+                        }
+                    umma_commit(gempty0 + 8 * gd);
+                }
+                __syncwarp();
+                if (++gd == P.gdepth) { gd = 0; gph ^= 1; }
+            }
+            if (lane == 0) umma_commit(tfull0 + 8 * as);
+            __syncwarp();
+            if (++as == P.acc_stages) { as = 0; aph ^= 1; }
+        }
+    } else if (warp >= EPI_WARP0 && warp < GATE_WARP0) {
+        // =========================================================================== epilogue
+        const int ew = warp - EPI_WARP0, lq = warp & 3, half = ew >> 2;
+        const int row = lq * 32 + lane;
+        const int ng = (P.N + 31) >> 5;
+        int as = 0; uint32_t aph = 0; bool first_tile = true;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long p = tile * TILE_M + row;
+            const bool valid = (p % P.blk_stride) < P.blk_valid;
+            const bool pair_valid = ((p & ~1ll) % P.blk_stride) < P.blk_valid;
+            mbar_wait(tfull0 + 8 * as, aph);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(as * P.nacc * P.acc_stride);
+#pragma unroll 1
+            for (int g = half; g < ng; g += 2) {
+                float s1 = 0.f, s2 = 0.f, pilot = 0.f;
+                const int nchunk = (P.N - g * 32) >= 32 ? 2 : 1;
+#pragma unroll 1
+                for (int c = 0; c < nchunk; ++c) {
+                    const int col0 = g * 32 + c * 16;
+                    if (P.epi == EPI_STATS_F32) {
+                        float v[16];
+                        tmem_ld16(t0 + col0, v);
+                        const float* bs = sbias + col0;
+                        if (c == 0) pilot = first_tile ? __shfl_sync(0xffffffffu, v[0] + bs[0], 0) : red[ew * MAXG + g].w;
+                        const bool st = col0 >= P.store_c0 && col0 < P.store_c1;
+                        float* o = P.out_f32 + (long long)(col0 - P.store_c0) * P.out_plane + p;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float y = v[i] + bs[i];
+                            if (st && valid) o[(long long)i * P.out_plane] = y;
+                            const float d = y - pilot;
+                            s1 += d; s2 = fmaf(d, d, s2);
+                        }
+                    } else if (P.acc_mode == ACC_POOL) {
+                        // AvgPool2 after the activation: the four 2x2 phases of this coarse pixel are the four accumulators
+                        float y[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) y[i] = 0.f;
+                        const float* bs = sbias + col0;
+#pragma unroll 1
+                        for (int a = 0; a < 4; ++a) {
+                            float v[16];
+                            tmem_ld16(t0 + (uint32_t)(a * P.acc_stride) + col0, v);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) y[i] += lrelu(v[i] + bs[i], P.slope);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const uint32_t w = split_bf16(valid ? 0.25f * y[i] : 0.f);
+                            const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
+                            const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
+                            __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)(col0 + i) * P.out_plane + (p & ~1ll);
+                            if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
+                        }
+                    } else {
+                        const int na = P.acc_mode == ACC_DECONV ? P.nacc : 1;
+#pragma unroll 1
+                        for (int a = 0; a < na; ++a) {
+                            float v[16];
+                            tmem_ld16(t0 + (uint32_t)(a * P.acc_stride) + col0, v);
+                            const float* bs = sbias + a * P.N + col0;
+                            const long long pa = p + (long long)a * P.out_acc_stride;
+                            if (P.epi == EPI_LRELU_F32) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (valid && col0 + i < P.store_c1) P.out_f32[(long long)(col0 + i) * P.out_plane + pa] = lrelu(v[i] + bs[i], P.slope);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) {
+                                    const uint32_t w = split_bf16(valid ? lrelu(v[i] + bs[i], P.slope) : 0.f);
+                                    const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
+                                    const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
+                                    __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)(col0 + i) * P.out_plane + (pa & ~1ll);
+                                    if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (P.epi == EPI_STATS_F32 && g < P.nstat) {
+                    const float ps = warp_sum(valid ? s1 : 0.f), pq = warp_sum(valid ? s2 : 0.f);
+                    const int cnt = __popc(__ballot_sync(0xffffffffu, valid)) * (nchunk * 16);
+                    if (lane == 0) {
+                        float4 r = red[ew * MAXG + g];
+                        r.x += (float)cnt; r.y += ps; r.z += pq; r.w = pilot;
+                        red[ew * MAXG + g] = r;
+                    }
+                    __syncwarp();
+                }
+            }
+            first_tile = false;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+            if (++as == P.acc_stages) { as = 0; aph ^= 1; }
+        }
+    } else if (GATED && warp >= GATE_WARP0) {
+        // =========================================================================== gate warps: r*h -> hi/lo operand
+        // task = one 16-byte piece (8 pixels of one channel): lanes cover 2 channel rows x 16 pieces (coalesced 256 B rows)
+        const int gt = tid - GATE_WARP0 * 32;
+        const int ntask = P.gate_ch * 16 / 128;
+        int gd = 0; uint32_t gph = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long p0 = tile * TILE_M;
+            mbar_wait(gempty0 + 8 * gd, gph ^ 1);
+            uint8_t* gb = sm + L.gbuf_off + (size_t)gd * (P.gate_ch / 32) * SLOT_BYTES;
+#pragma unroll 1
+            for (int t0 = 0; t0 < ntask; t0 += 4) {
+                uint4 hi[4], lo[4]; float4 g0[4], g1[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = (t0 + q) * 128 + gt, ch = idx >> 4, j = idx & 15;
+                    const long long e = (long long)ch * P.gate_h_plane + p0 + 8 * j;
+                    hi[q] = __ldg(reinterpret_cast<const uint4*>(P.gate_h + e));
+                    lo[q] = __ldg(reinterpret_cast<const uint4*>(P.gate_h + P.gate_h_lo + e));
+                    const float4* gp = reinterpret_cast<const float4*>(P.gate_pre + (long long)ch * P.gate_pre_plane + p0 + 8 * j);
+                    g0[q] = __ldg(gp); g1[q] = __ldg(gp + 1);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int idx = (t0 + q) * 128 + gt, ch = idx >> 4, j = idx & 15;
+                    const float sc = sgaff[2 * ch], sh = sgaff[2 * ch + 1];
+                    const uint32_t hw[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w}, lw[4] = {lo[q].x, lo[q].y, lo[q].z, lo[q].w};
+                    const float gv[8] = {g0[q].x, g0[q].y, g0[q].z, g0[q].w, g1[q].x, g1[q].y, g1[q].z, g1[q].w};
+                    uint32_t oh[4], ol[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float h0 = bf16lo_to_f32(hw[u]) + bf16lo_to_f32(lw[u]), h1 = bf16hi_to_f32(hw[u]) + bf16hi_to_f32(lw[u]);
+                        const uint32_t w0 = split_bf16(h0 * sigmoid_fast(fmaf(gv[2 * u], sc, sh)));
+                        const uint32_t w1 = split_bf16(h1 * sigmoid_fast(fmaf(gv[2 * u + 1], sc, sh)));
+                        oh[u] = (w0 & 0xFFFFu) | (w1 << 16);
+                        ol[u] = (w0 >> 16) | (w1 & 0xFFFF0000u);
+                    }
+                    const int cu = ch & 31;
+                    uint8_t* d = gb + (size_t)(ch >> 5) * SLOT_BYTES + (j >> 3) * 8192 + cu * 128 + (((j & 7) ^ (cu & 7)) << 4);
+                    *reinterpret_cast<uint4*>(d) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                    *reinterpret_cast<uint4*>(d + 4096) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(gfull0 + 8 * gd);
+            if (++gd == P.gdepth) { gd = 0; gph ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (P.epi == EPI_STATS_F32 && P.nstat > 0) {
+        for (int i = tid; i < NWARP_EPI * P.nstat; i += nthreads) {
+            const int ew = i / P.nstat, g = i % P.nstat;
+            P.sink.partial[(size_t)g * P.sink.stride + (size_t)blockIdx.x * NWARP_EPI + ew] = red[ew * MAXG + g];
+        }
+    }
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
+    if (P.epi == EPI_STATS_F32 && P.nstat > 0) stats2_finalize_last_cta(P.sink, NWARP_EPI * gridDim.x, gridDim.x, &P.aff);
+}
+
+// ---- weight images: hi and lo bf16 parts of W^T, K-major rows of 128 bytes (64 channels), SWIZZLE_128B
+struct WImgSpec {
+    const float* W; long long w_ld, w_ks;     // element (row n, channel k) = W[(n % racc)*w_ld + (n / racc)*w_acc + k*w_ks]
+    long long w_acc; int racc;                // rows per accumulator block (ConvTranspose phases); racc >= nrows: plain matrix
+    int nrows, nrows_valid, K, k_skip;        // k_skip: leading source columns that are not part of the contraction
+    unsigned long long off;                   // byte offset of the image in the arena
+};
+constexpr int WIMG_MAX = 32;
+struct WImgBatch { WImgSpec s[WIMG_MAX]; int n; char* base; };
+
+__global__ void __launch_bounds__(256) wimg_kernel(const WImgBatch B) {
+    const WImgSpec& S = B.s[blockIdx.y];
+    const int nkb = (S.K + 63) / 64;
+    const int chunks_per_row = nkb * 8, total = S.nrows * chunks_per_row;
+    const size_t lo_off = (size_t)nkb * S.nrows * 128;
+    char* img = B.base + S.off;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int n = idx / chunks_per_row, ch = idx % chunks_per_row;
+        const int kb = ch >> 3, j = ch & 7, k0 = kb * 64 + j * 8;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = k0 + 2 * u + e;
+                v[e] = (k < S.K && n < S.nrows_valid)
+                           ? __ldg(S.W + (long long)(n % S.racc) * S.w_ld + (long long)(n / S.racc) * S.w_acc + (long long)(k + S.k_skip) * S.w_ks) : 0.f;
+            }
+            const uint32_t w0 = split_bf16(v[0]), w1 = split_bf16(v[1]);
+            h[u] = (w0 & 0xFFFFu) | (w1 << 16);
+            l[u] = (w0 >> 16) | (w1 & 0xFFFF0000u);
+        }
+        const size_t o = (size_t)kb * S.nrows * 128 + (size_t)n * 128 + ((j ^ (n & 7)) << 4);
+        *reinterpret_cast<uint4*>(img + o) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(img + lo_off + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+static inline size_t wimg_bytes(int nrows, int K) { return 2 * (size_t)((K + 63) / 64) * nrows * 128; }
+
+}  // namespace v2
+}  // namespace urnn

@@ -81,7 +81,7 @@ constexpr int COMM_RING = 64;        // exchanges in flight are at most 1 apart 
 constexpr int COMM_MAX_SETS = 8;     // statistics sets per exchange (<= 8 GroupNorm groups / 2 LayerNorms)
 struct CommDev {
     int world, rank;                               // world <= 1: no exchange
-    double2*  slots[COMM_MAX_WORLD];               // peer p: slots[p][(ring*world + src_rank)*COMM_MAX_SETS + set]
+    double4*  slots[COMM_MAX_WORLD];               // peer p: slots[p][(ring*world + src_rank)*COMM_MAX_SETS + set]
     unsigned* flags[COMM_MAX_WORLD];               // peer p: flags[p][ring*world + src_rank] = epoch
     unsigned* seq;                                 // local exchange counter (device memory)
 };
@@ -117,7 +117,7 @@ __device__ __forceinline__ void stats_exchange(const StatSink& s) {
     // 1. my totals -> slot `rank` of every rank (including myself)
     for (int i = threadIdx.x; i < c.world * s.nsets; i += blockDim.x) {
         const int peer = i / s.nsets, set = i % s.nsets;
-        c.slots[peer][slot0 + set] = s.total[set];
+        c.slots[peer][slot0 + set] = make_double4(s.total[set].x, s.total[set].y, 0.0, 0.0);
     }
     __threadfence_system();
     __syncthreads();
@@ -132,7 +132,7 @@ __device__ __forceinline__ void stats_exchange(const StatSink& s) {
     if (threadIdx.x < s.nsets) {
         double a = 0.0, b = 0.0;
         for (int r = 0; r < c.world; ++r) {
-            const volatile double2* src = c.slots[c.rank] + (int)(ring * c.world + r) * COMM_MAX_SETS + threadIdx.x;
+            const volatile double4* src = c.slots[c.rank] + (int)(ring * c.world + r) * COMM_MAX_SETS + threadIdx.x;
             a += src->x; b += src->y;
         }
         s.total[threadIdx.x] = make_double2(a, b);
