@@ -134,6 +134,8 @@ static int run_case(const Case& cs, int num_sms) {
         P.aff.scale = d_scale; P.aff.shift = d_shift; P.aff.gamma = d_gamma; P.aff.beta = d_beta; P.aff.channels = cs.nstat * 32; P.aff.ch_per_set = 32; P.aff.eps = 1e-5f;
     }
     OK(plan_gemm(L, num_sms));
+    long long* d_dbg = nullptr;
+    if (getenv("V2_TRACE")) { CK(cudaMalloc(&d_dbg, (9 * 32 + 768) * 8)); CK(cudaMemset(d_dbg, 0, (9 * 32 + 768) * 8)); }
     printf("   grid %d smem %zu nslots %d gdepth %d tmem %d stages %d nsteps %d\n", L.grid, L.smem, P.nslots, P.gdepth, P.tmem_cols, P.acc_stages, P.nsteps); fflush(stdout);
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     OK(launch_gemm(L, 0, false));
@@ -147,6 +149,24 @@ static int run_case(const Case& cs, int num_sms) {
     const double out_bytes = 4.0 * outC * out_ntot;
     printf("   %.1f us per launch, %.0f GB/s (in %.1f MB + out %.1f MB)\n", ms * 200.0, (in_bytes + out_bytes) / (ms / 5 * 1e-3) * 1e-9, in_bytes * 1e-6, out_bytes * 1e-6);
 
+    if (d_dbg) {
+        P.dbg = d_dbg; OK(launch_gemm(L, 0, false)); CK(cudaDeviceSynchronize()); P.dbg = nullptr;
+        long long h[9 * 32 + 768]; CK(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        {
+            long long tmin = 1LL << 62; for (int b = 0; b < L.grid; ++b) if (h[9 * 32 + b] < tmin) tmin = h[9 * 32 + b];
+            printf("   per CTA (start us, end us, smid):");
+            for (int b = 0; b < L.grid; b += 7) printf(" [%d: %.1f %.1f sm%lld]", b, (h[9 * 32 + b] - tmin) * 1e-3, (h[9 * 32 + 256 + b] - tmin) * 1e-3, h[9 * 32 + 512 + b]);
+            double emax = 0, emin = 1e30; for (int b = 0; b < L.grid; ++b) { double e = (h[9 * 32 + 256 + b] - tmin) * 1e-3; if (e > emax) emax = e; if (e < emin) emin = e; }
+            printf("\n   CTA end times: min %.1f us max %.1f us\n", emin, emax);
+        }
+        const long long t0 = h[8 * 32];
+        printf("   timeline of CTA 0 (cycles since setup done): tile: tma_first tma_last | mma_tempty mma_full0 mma_fullN mma_commit | epi_wake epi_done\n");
+        for (int t = 0; t < 14; ++t) {
+            printf("   %2d:", t);
+            for (int e = 0; e < 8; ++e) printf(" %7lld%s", h[e * 32 + t] ? h[e * 32 + t] - t0 : -1, (e == 1 || e == 5) ? " |" : "");
+            printf("\n");
+        }
+    }
     // ---- host reference on a sample of pixels
     std::vector<float> out_h; std::vector<uint16_t> split_h;
     if (d_out) { out_h.resize((size_t)outC * out_ntot); CK(cudaMemcpy(out_h.data(), d_out, out_h.size() * 4, cudaMemcpyDeviceToHost)); }
@@ -170,7 +190,7 @@ static int run_case(const Case& cs, int num_sms) {
         return s;
     };
     double maxerr = 0, maxref = 0; long long nbad = 0, nchk = 0, npadbad = 0;
-    const long long stepp = cs.ntot > 4096 ? 37 : 1;
+    const long long stepp = cs.ntot > 100000 ? 997 : (cs.ntot > 4096 ? 37 : 1);
     for (long long p = 0; p < cs.ntot; p += stepp) {
         const bool valid = (p % cs.blk_stride) < cs.blk_valid;
         for (int n = 0; n < cs.N; ++n) {
@@ -232,6 +252,22 @@ int main(int argc, char** argv) {
         {"final stem 64 -> 16 fp32", 1, {64, 0, 0}, 0, 16, 1, ACC_SINGLE, EPI_LRELU_F32, big, big, big - 3, 0},
         {"plain stem 96 -> 96 split", 1, {96, 0, 0}, 0, 96, 1, ACC_SINGLE, EPI_LRELU_SPLIT, 30 * 128, 30 * 128, 30 * 128 - 1, 0},
     };
+    const long long full = 16LL * 123 * 128;               // location1 grid in the phase-separated layout
+    Case perf[] = {
+        {"PERF enc1 sweep A", 2, {16, 64, 0}, 0, 128, 1, ACC_SINGLE, EPI_STATS_F32, full, 123 * 128, 15625, 4},
+        {"PERF enc1 sweep B gated", 1, {16, 0, 0}, 64, 64, 1, ACC_SINGLE, EPI_STATS_F32, full, 123 * 128, 15625, 2},
+        {"PERF dec1 sweep A", 3, {96, 64, 64}, 0, 128, 1, ACC_SINGLE, EPI_STATS_F32, full, 123 * 128, 15625, 4},
+        {"PERF dec1 sweep B gated", 2, {96, 64, 0}, 64, 64, 1, ACC_SINGLE, EPI_STATS_F32, full, 123 * 128, 15625, 2},
+        {"PERF stage-2 pooled stem 64 -> 64", 1, {64, 0, 0}, 0, 64, 4, ACC_POOL, EPI_LRELU_SPLIT, full / 4, 123 * 128, 15625, 0},
+        {"PERF deconv half 96 -> 2 x 96 (half res -> full res)", 1, {96, 0, 0}, 0, 96, 2, ACC_DECONV, EPI_LRELU_SPLIT, full / 4, 123 * 128, 15625, 0},
+        {"PERF final stem 64 -> 16", 1, {64, 0, 0}, 0, 16, 1, ACC_SINGLE, EPI_LRELU_F32, full, 123 * 128, 15625, 0},
+    };
+    if (argc > 1 && !strcmp(argv[1], "perf")) {
+        int f = 0;
+        int pi = 0;
+        for (const Case& c : perf) { if (argc < 3 || atoi(argv[2]) == pi) f += run_case(c, num_sms); ++pi; }
+        return f ? 1 : 0;
+    }
     int fails = 0, i = 0;
     for (const Case& c : cases) { if (only < 0 || only == i) fails += run_case(c, num_sms); ++i; }
     printf("%s (%d failing cases)\n", fails ? "SELFTEST FAILED" : "SELFTEST PASSED", fails);

@@ -11,8 +11,8 @@
 // candidate GEMM (K = F channels), written by four gate warps.  Weights are resident in shared memory as a hi and a lo
 // image (K-major SWIZZLE_128B), prepared once per sequence.
 //
-// One persistent CTA per SM:  warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM owner, warps 4-11 epilogue
-// (tcgen05.ld: lane = pixel, column = output channel), warps 12-15 gate warps (gated launches only).
+// One persistent CTA per SM:  warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM owner, warps 4-19 epilogue
+// (tcgen05.ld: lane = pixel, column = output channel), warps 20-23 gate warps (gated launches only).
 // Pipelines: operand ring (full/empty), gated-operand buffers (gfull/gempty), accumulator stages (tfull/tempty).
 #pragma once
 #include <cuda.h>
@@ -28,8 +28,8 @@ constexpr int TILE_M = 128;
 constexpr int SLOT_BYTES = 16384;         // one ring slot: 32 channels x 128 pixels x {hi,lo} bf16
 constexpr int MAX_STEPS = 16;
 constexpr int MAXG = 8;                   // 32-column groups per accumulator (N <= 256)
-constexpr int NWARP_EPI = 8;
-constexpr int EPI_WARP0 = 4, GATE_WARP0 = 12;
+constexpr int NWARP_EPI = 16;
+constexpr int EPI_WARP0 = 4, GATE_WARP0 = 20;
 constexpr int NTHREADS_PLAIN = 32 * GATE_WARP0, NTHREADS_GATED = 32 * (GATE_WARP0 + 4);
 constexpr size_t SMEM_MAX = 231424;       // 227 KB opt-in limit minus 1 KB for static shared memory
 
@@ -44,7 +44,7 @@ struct StatSink2 {
     double*   total;     // [nsets][4] = (mean, M2, n, -)
     unsigned* counter;
     int       nsets;
-    int       stride;    // >= NWARP_EPI * CTAs
+    int       stride;    // >= CTAs
     CommDev   comm;
 };
 
@@ -102,25 +102,25 @@ __device__ __forceinline__ void stats2_finalize_last_cta(const StatSink2& s, int
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // one warp per set; the partials (one per CTA) are re-referenced to the first partial's pilot K00 in double -- only
+    // multiplies and adds, no divisions in the loop (a single warp runs ~8 cycles per dependent instruction) -- and summed
+    // in a fixed order: lane-strided, then a fixed shuffle tree.
     const int nwarp = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int set = warp; set < s.nsets; set += nwarp) {
-        double n = 0.0, mean = 0.0, m2 = 0.0;
+        const double k00 = (double)__ldcg(&s.partial[(size_t)set * s.stride]).w;
+        double n = 0.0, a1 = 0.0, a2 = 0.0;
         for (int i = lane; i < ncontrib; i += 32) {
             const float4 v = __ldcg(&s.partial[(size_t)set * s.stride + i]);
-            if (v.x > 0.f) {
-                const double nb = (double)v.x, s1 = (double)v.y, s2 = (double)v.z;
-                chan_merge(n, mean, m2, nb, (double)v.w + s1 / nb, s2 - s1 * s1 / nb);
-            }
+            const double nb = (double)v.x, s1 = (double)v.y, s2 = (double)v.z, d = (double)v.w - k00;
+            n += nb; a1 += s1 + nb * d; a2 += s2 + 2.0 * d * s1 + nb * d * d;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {          // fixed tree: deterministic
-            const double nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
-                         qb = __shfl_xor_sync(0xffffffffu, m2, o);
-            // both partners must compute the same result: merge in (lower lane, higher lane) order
-            if (lane & o) { double n2 = nb, me2 = mb, q2 = qb; chan_merge(n2, me2, q2, n, mean, m2); n = n2; mean = me2; m2 = q2; }
-            else chan_merge(n, mean, m2, nb, mb, qb);
+        n = warp_sum(n); a1 = warp_sum(a1); a2 = warp_sum(a2);
+        if (lane == 0) {
+            const double m = n > 0.0 ? a1 / n : 0.0;
+            double m2 = a2 - a1 * m;                 // sum (x - mean)^2
+            if (m2 < 0.0) m2 = 0.0;
+            s.total[4 * set] = k00 + m; s.total[4 * set + 1] = m2; s.total[4 * set + 2] = n;
         }
-        if (lane == 0) { s.total[4 * set] = mean; s.total[4 * set + 1] = m2; s.total[4 * set + 2] = n; }
     }
     __syncthreads();
     stats2_exchange(s);
@@ -175,10 +175,12 @@ struct GemmParams {
     __nv_bfloat16* out_hi; long long out_lo;       // split map destination: hi planes, lo planes out_lo elements further
     long long out_acc_stride;                      // ACC_DECONV: pixel offset between the destination blocks of the accumulators
     int nstat; StatSink2 sink; AffineOut aff;      // leading 32-column groups with GroupNorm statistics
+    int l2_ahead;                                  // tiles of L2 prefetch distance (0: off)
+    long long* dbg;                                // bring-up: clock64 stamps of CTA 0, [event 0..7][tile 0..31]
     int nslots, tmem_cols, acc_stages, acc_stride; // ring depth; TMEM allocation; stages and column stride between accumulators
 };
 
-struct SmemPlan { uint32_t w_off, ring_off, gbuf_off, bias_off, gaff_off, bar_off, red_off, total; };
+struct SmemPlan { uint32_t w_off, ring_off, gbuf_off, bias_off, gaff_off, bar_off, red_off, ptab_off, mtab_off, total; };
 
 __host__ __device__ inline SmemPlan smem_plan(int nkb, int nrows, int nslots, int gate_ch, int gdepth, int ncols_total) {
     SmemPlan s;
@@ -190,9 +192,16 @@ __host__ __device__ inline SmemPlan smem_plan(int nkb, int nrows, int nslots, in
     s.gaff_off = o; o += ((uint32_t)gate_ch * 8u + 127u) & ~127u;
     s.bar_off = o; o += 512;
     s.red_off = o; o += NWARP_EPI * MAXG * 16;
+    s.ptab_off = o; o += MAX_STEPS * 32;            // producer table
+    s.mtab_off = o; o += MAX_STEPS * 2 * 32;        // MMA table (one entry per K=16 group)
     s.total = o + 1024;      // alignment slack
     return s;
 }
+
+// Per-step tables in shared memory: the single-thread control roles run one dependent instruction every ~7 cycles, so
+// everything that can be precomputed is (measured: 1500 cycles per step with descriptors built in the loop).
+struct ProdEnt { unsigned long long map; int c0; int pix_off; unsigned half_bytes; unsigned pad[3]; };          // 32 B
+struct MmaEnt { unsigned long long a_hi, b_hi; unsigned a_lo_delta, acc_col, first, pad; };                     // 32 B
 
 template <bool GATED>
 __global__ void __launch_bounds__(GATED ? NTHREADS_GATED : NTHREADS_PLAIN, 1)
@@ -202,7 +211,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* sm = smem_raw + (base - raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform (uniform registers for TMEM / MMA operands)
     const int nthreads = GATED ? NTHREADS_GATED : NTHREADS_PLAIN;
     const int ncols_total = P.acc_mode == ACC_DECONV ? P.nacc * P.N : P.N;
     const SmemPlan L = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total);
@@ -228,6 +238,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), (uint32_t)P.tmem_cols);
     for (int i = tid; i < NWARP_EPI * MAXG; i += nthreads) red[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < ncols_total; i += nthreads) sbias[i] = (P.bias != nullptr && i < P.nbias) ? __ldg(P.bias + (i % P.bias_mod)) : 0.f;
+    ProdEnt* ptab = reinterpret_cast<ProdEnt*>(sm + L.ptab_off);
+    if (tid < P.nsteps) {
+        const Step& st = P.steps[tid];
+        const uint32_t hl = P.nmma == 3 ? 2u : 1u;
+        ProdEnt pe;
+        pe.map = reinterpret_cast<unsigned long long>(st.map == 0 ? (const void*)&map0 : (st.map == 1 ? (const void*)&map1 : (const void*)&map2));
+        pe.c0 = st.c0; pe.pix_off = (int)st.pix_off; pe.half_bytes = (uint32_t)st.unit_ch * 128u * hl; pe.pad[0] = pe.pad[1] = pe.pad[2] = 0;
+        ptab[tid] = pe;
+    }
     {
         const int nvec = 2 * P.nkb * P.nrows * 8;            // 16-byte pieces of the weight image
         const char* src = reinterpret_cast<const char*>(P.wimg);
@@ -249,61 +268,77 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         for (int i = tid; i < P.gate_ch; i += nthreads) { sgaff[2 * i] = __ldg(P.gate_scale + i); sgaff[2 * i + 1] = __ldg(P.gate_shift + i); }
         __syncthreads();
     }
+#define V2_STAMP(ev, ti) do { if (P.dbg && blockIdx.x == 0 && lane == 0 && (ti) < 32) P.dbg[(ev) * 32 + (ti)] = clock64(); } while (0)
     const long long ntiles = P.ntot / TILE_M;
+    if (P.dbg && blockIdx.x == 0 && tid == 0) P.dbg[8 * 32] = clock64();
+    if (P.dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); P.dbg[9 * 32 + blockIdx.x] = (long long)t_; unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); P.dbg[9 * 32 + 512 + blockIdx.x] = sm_; }
     const uint32_t wlo = (uint32_t)P.nkb * P.nrows * 128u;   // lo image offset
 
-    if (warp == 0) {
-        // =========================================================================== TMA producer
+    if (warp == 0 || warp == 3) {
+        // =========================================================================== TMA producers (two: even / odd units)
         if (lane == 0) {
-            int slot = 0; uint32_t ph = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const long long p0 = tile * TILE_M;
-                for (int s = 0; s < P.nsteps; ++s) {
-                    const Step& st = P.steps[s];
-                    mbar_wait(empty0 + 8 * slot, ph ^ 1);
-                    const uint32_t dst = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
-                    const uint32_t bar = full0 + 8 * slot;
-                    const uint32_t half_bytes = (uint32_t)st.unit_ch * 128u * (P.nmma == 3 ? 2u : 1u);
-                    mbar_arrive_expect_tx(bar, 2u * half_bytes);
-                    const void* m = st.map == 0 ? (const void*)&map0 : (st.map == 1 ? (const void*)&map1 : (const void*)&map2);
-                    const int px = (int)(p0 + st.pix_off);
-                    tma_load_3d(dst, m, bar, px, st.c0, 0, L2_EVICT_NORMAL);
-                    tma_load_3d(dst + half_bytes, m, bar, px + 64, st.c0, 0, L2_EVICT_NORMAL);
-                    if (++slot == P.nslots) { slot = 0; ph ^= 1; }
-                }
+            const int me = warp == 0 ? 0 : 1;
+            int slot = me; uint32_t ph = 0;
+            if (slot >= P.nslots) { slot -= P.nslots; ph ^= 1; }
+            int s = me;                                      // step inside the tile
+            long long tile = blockIdx.x;
+            while (s >= P.nsteps) { s -= P.nsteps; tile += gridDim.x; }
+            int ti = 0;
+            while (tile < ntiles) {
+                const ProdEnt pe = ptab[s];
+                const int px = (int)(tile * TILE_M) + pe.pix_off;
+                mbar_wait(empty0 + 8 * slot, ph ^ 1);
+                const uint32_t dst = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
+                const uint32_t bar = full0 + 8 * slot;
+                mbar_arrive_expect_tx(bar, 2u * pe.half_bytes);
+                tma_load_3d(dst, reinterpret_cast<const void*>(pe.map), bar, px, pe.c0, 0, L2_EVICT_NORMAL);
+                tma_load_3d(dst + pe.half_bytes, reinterpret_cast<const void*>(pe.map), bar, px + 64, pe.c0, 0, L2_EVICT_NORMAL);
+                if (s <= 1) V2_STAMP(0 + me, ti);
+                slot += 2; if (slot >= P.nslots) { slot -= P.nslots; ph ^= 1; }
+                s += 2; while (s >= P.nsteps) { s -= P.nsteps; tile += gridDim.x; ++ti; }
             }
         }
     } else if (warp == 1) {
         // =========================================================================== MMA issuer
+        // The whole warp walks the pipeline with warp-uniform values (descriptors live in uniform registers); one elected
+        // lane issues tcgen05.mma / tcgen05.commit.
         const uint32_t idesc = instr_desc_bf16(P.N);
         int slot = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0; int gd = 0; uint32_t gph = 0;
         const uint32_t hl = P.nmma == 3 ? 2u : 1u;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t wlo16 = wlo >> 4;
+        int ti = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             mbar_wait(tempty0 + 8 * as, aph ^ 1);
             tc_fence_after();
+            V2_STAMP(2, ti);
             const uint32_t d0 = tmem_base + (uint32_t)(as * P.nacc * P.acc_stride);
             for (int s = 0; s < P.nsteps; ++s) {
-                const Step& st = P.steps[s];
+                const int unit_ch = P.steps[s].unit_ch, kg = P.steps[s].kglob, acc = P.steps[s].acc;
                 mbar_wait(full0 + 8 * slot, ph);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_base = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
-                    const uint32_t lbo = (uint32_t)st.unit_ch * 128u * hl, lo_off = (uint32_t)st.unit_ch * 128u;
-                    for (int j = 0; j < (st.unit_ch >> 4); ++j) {
-                        const int k = st.kglob + 16 * j;
-                        const uint32_t b_base = base + L.w_off + (uint32_t)(k >> 6) * P.nrows * 128u + (uint32_t)((k & 63) >> 4) * 32u;
-                        const uint64_t a_hi = smem_desc_mn_sw128(a_base + j * 2048, lbo);
-                        const uint64_t a_lo = smem_desc_mn_sw128(a_base + lo_off + j * 2048, lbo);
-                        const int na = P.acc_mode == ACC_DECONV ? P.nacc : 1;
-                        for (int a = 0; a < na; ++a) {
-                            const int acc = P.acc_mode == ACC_DECONV ? a : st.acc;
+                if (s == 0) V2_STAMP(3, ti);
+                if (s == P.nsteps - 1) V2_STAMP(4, ti);
+                const uint32_t a_base = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
+                const uint64_t a0 = smem_desc_mn_sw128(a_base, (uint32_t)unit_ch * 128u * hl);
+                const uint32_t a_lo_delta = ((uint32_t)unit_ch * 128u) >> 4;
+                const uint64_t b0 = smem_desc_sw128(base + L.w_off + (uint32_t)(kg >> 6) * P.nrows * 128u + (uint32_t)((kg & 63) >> 4) * 32u);
+                const int kg1 = kg + 16;               // the second K=16 group may start the next 64-channel weight block
+                const uint64_t b1 = smem_desc_sw128(base + L.w_off + (uint32_t)(kg1 >> 6) * P.nrows * 128u + (uint32_t)((kg1 & 63) >> 4) * 32u);
+                const uint32_t first0 = (P.acc_mode == ACC_POOL ? kg : s) == 0 ? 0u : 1u;
+                if (elect_one()) {
+                    for (int j = 0; j < (unit_ch >> 4); ++j) {
+                        const uint64_t a_hi = a0 + (uint32_t)(j * 128), a_lo = a_hi + a_lo_delta, b_hi = j == 0 ? b0 : b1;
+                        const uint32_t first = j == 0 ? first0 : 1u;
+                        if (P.acc_mode != ACC_DECONV) {
                             const uint32_t d = d0 + (uint32_t)(acc * P.acc_stride);
-                            const uint32_t b = b_base + (uint32_t)(a * P.N) * 128u;
-                            const uint32_t first = (P.acc_mode == ACC_POOL ? k : (s | j)) == 0 ? 0u : 1u;
-                            umma_f16(d, a_hi, smem_desc_sw128(b), idesc, first);
-                            if (P.nmma == 3) {
-                                umma_f16(d, a_lo, smem_desc_sw128(b), idesc, 1u);
-                                umma_f16(d, a_hi, smem_desc_sw128(b + wlo), idesc, 1u);
+                            umma_f16(d, a_hi, b_hi, idesc, first);
+                            if (P.nmma == 3) { umma_f16(d, a_lo, b_hi, idesc, 1u); umma_f16(d, a_hi, b_hi + wlo16, idesc, 1u); }
+                        } else {
+                            for (int a = 0; a < P.nacc; ++a) {
+                                const uint32_t d = d0 + (uint32_t)(a * P.acc_stride);
+                                const uint64_t b = b_hi + (uint32_t)((a * P.N * 128) >> 4);
+                                umma_f16(d, a_hi, b, idesc, first);
+                                if (P.nmma == 3) { umma_f16(d, a_lo, b, idesc, 1u); umma_f16(d, a_hi, b + wlo16, idesc, 1u); }
                             }
                         }
                     }
@@ -315,125 +350,137 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
             if constexpr (GATED) {
                 mbar_wait(gfull0 + 8 * gd, gph);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t g_base = base + L.gbuf_off + (uint32_t)gd * (P.gate_ch / 32) * SLOT_BYTES;
+                const uint32_t g_base = base + L.gbuf_off + (uint32_t)gd * (P.gate_ch / 32) * SLOT_BYTES;
+                if (elect_one()) {
                     for (int u = 0; u < P.gate_ch / 32; ++u)
                         for (int j = 0; j < 2; ++j) {
                             const int k = P.gate_k0 + 32 * u + 16 * j;
-                            const uint32_t b = base + L.w_off + (uint32_t)(k >> 6) * P.nrows * 128u + (uint32_t)((k & 63) >> 4) * 32u;
+                            const uint64_t b = smem_desc_sw128(base + L.w_off + (uint32_t)(k >> 6) * P.nrows * 128u + (uint32_t)((k & 63) >> 4) * 32u);
                             const uint32_t a = g_base + (uint32_t)u * SLOT_BYTES + j * 2048;
-                            const uint64_t a_hi = smem_desc_mn_sw128(a, 8192), a_lo = smem_desc_mn_sw128(a + 4096, 8192);
+                            const uint64_t a_hi = smem_desc_mn_sw128(a, 8192), a_lo = a_hi + (4096 >> 4);
                             const uint32_t first = (P.nsteps == 0 && (u | j) == 0) ? 0u : 1u;
-                            umma_f16(d0, a_hi, smem_desc_sw128(b), idesc, first);
-                            if (P.nmma == 3) {
-                                umma_f16(d0, a_lo, smem_desc_sw128(b), idesc, 1u);
-                                umma_f16(d0, a_hi, smem_desc_sw128(b + wlo), idesc, 1u);
-                            }
+                            umma_f16(d0, a_hi, b, idesc, first);
+                            if (P.nmma == 3) { umma_f16(d0, a_lo, b, idesc, 1u); umma_f16(d0, a_hi, b + wlo16, idesc, 1u); }
                         }
                     umma_commit(gempty0 + 8 * gd);
                 }
                 __syncwarp();
                 if (++gd == P.gdepth) { gd = 0; gph ^= 1; }
             }
-            if (lane == 0) umma_commit(tfull0 + 8 * as);
+            if (elect_one()) umma_commit(tfull0 + 8 * as);
+            V2_STAMP(5, ti);
             __syncwarp();
             if (++as == P.acc_stages) { as = 0; aph ^= 1; }
         }
     } else if (warp >= EPI_WARP0 && warp < GATE_WARP0) {
         // =========================================================================== epilogue
-        const int ew = warp - EPI_WARP0, lq = warp & 3, half = ew >> 2;
+        // 16 warps: lane quarter lq = warp & 3 (hardware: a warp reads TMEM lanes 32*(warp%4)..), column chunks of 16
+        // are dealt round-robin to the four warps of a lane quarter.  A 32-column GroupNorm group is two chunks, usually
+        // on two different warps: every (warp, group) keeps its own partial (n, S1, S2, pilot), merged by the finalizer.
+        const int ew = warp - EPI_WARP0, lq = warp & 3, qtr = ew >> 2;
         const int row = lq * 32 + lane;
-        const int ng = (P.N + 31) >> 5;
+        const int nchunks = P.N >> 4;
+        const unsigned tiles_per_blk = (unsigned)(P.blk_stride / TILE_M);
         int as = 0; uint32_t aph = 0; bool first_tile = true;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long p = tile * TILE_M + row;
-            const bool valid = (p % P.blk_stride) < P.blk_valid;
-            const bool pair_valid = ((p & ~1ll) % P.blk_stride) < P.blk_valid;
+            const unsigned in_blk = ((unsigned)tile % tiles_per_blk) * TILE_M + row;
+            const bool valid = in_blk < (unsigned)P.blk_valid;
+            const bool pair_valid = (in_blk & ~1u) < (unsigned)P.blk_valid;
             mbar_wait(tfull0 + 8 * as, aph);
             tc_fence_after();
+            if (ew == 0 && lane == 0) V2_STAMP(6, (int)((tile - blockIdx.x) / gridDim.x));
             const uint32_t t0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(as * P.nacc * P.acc_stride);
 #pragma unroll 1
-            for (int g = half; g < ng; g += 2) {
-                float s1 = 0.f, s2 = 0.f, pilot = 0.f;
-                const int nchunk = (P.N - g * 32) >= 32 ? 2 : 1;
-#pragma unroll 1
-                for (int c = 0; c < nchunk; ++c) {
-                    const int col0 = g * 32 + c * 16;
-                    if (P.epi == EPI_STATS_F32) {
-                        float v[16];
-                        tmem_ld16(t0 + col0, v);
-                        const float* bs = sbias + col0;
-                        if (c == 0) pilot = first_tile ? __shfl_sync(0xffffffffu, v[0] + bs[0], 0) : red[ew * MAXG + g].w;
-                        const bool st = col0 >= P.store_c0 && col0 < P.store_c1;
+            for (int c = qtr; c < nchunks; c += 4) {
+                const int col0 = c * 16;
+                if (P.epi == EPI_STATS_F32) {
+                    float v[16];
+                    tmem_ld16(t0 + col0, v);
+                    const float4* bs4 = reinterpret_cast<const float4*>(sbias + col0);
+                    float bsv[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { const float4 b = bs4[i]; bsv[4 * i] = b.x; bsv[4 * i + 1] = b.y; bsv[4 * i + 2] = b.z; bsv[4 * i + 3] = b.w; }
+                    const int g = c >> 1;
+                    float pilot = 0.f;
+                    if (g < P.nstat) pilot = first_tile ? __shfl_sync(0xffffffffu, v[0] + bsv[0], 0) : red[ew * MAXG + g].w;
+                    float y[16], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        y[i] = v[i] + bsv[i];
+                        const float d = v[i] + (bsv[i] - pilot);
+                        s1 += d; s2 = fmaf(d, d, s2);
+                    }
+                    if (col0 >= P.store_c0 && col0 < P.store_c1 && valid) {
                         float* o = P.out_f32 + (long long)(col0 - P.store_c0) * P.out_plane + p;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float y = v[i] + bs[i];
-                            if (st && valid) o[(long long)i * P.out_plane] = y;
-                            const float d = y - pilot;
-                            s1 += d; s2 = fmaf(d, d, s2);
+                        for (int i = 0; i < 16; ++i) { *o = y[i]; o += P.out_plane; }
+                    }
+                    if (g < P.nstat) {
+                        const float ps = warp_sum(valid ? s1 : 0.f), pq = warp_sum(valid ? s2 : 0.f);
+                        const int cnt = __popc(__ballot_sync(0xffffffffu, valid)) * 16;
+                        if (lane == 0) {
+                            float4 r = red[ew * MAXG + g];
+                            r.x += (float)cnt; r.y += ps; r.z += pq; r.w = pilot;
+                            red[ew * MAXG + g] = r;
                         }
-                    } else if (P.acc_mode == ACC_POOL) {
-                        // AvgPool2 after the activation: the four 2x2 phases of this coarse pixel are the four accumulators
-                        float y[16];
+                        __syncwarp();
+                    }
+                } else if (P.acc_mode == ACC_POOL) {
+                    // AvgPool2 after the activation: the four 2x2 phases of this coarse pixel are the four accumulators
+                    float y[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) y[i] = 0.f;
-                        const float* bs = sbias + col0;
+                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
+                    const float* bs = sbias + col0;
 #pragma unroll 1
-                        for (int a = 0; a < 4; ++a) {
-                            float v[16];
-                            tmem_ld16(t0 + (uint32_t)(a * P.acc_stride) + col0, v);
+                    for (int a = 0; a < 4; ++a) {
+                        float v[16];
+                        tmem_ld16(t0 + (uint32_t)(a * P.acc_stride) + col0, v);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) y[i] += lrelu(v[i] + bs[i], P.slope);
-                        }
+                        for (int i = 0; i < 16; ++i) y[i] += lrelu(v[i] + bs[i], P.slope);
+                    }
+                    __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)col0 * P.out_plane + (p & ~1ll);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const uint32_t w = split_bf16(valid ? 0.25f * y[i] : 0.f);
-                            const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
-                            const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
-                            __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)(col0 + i) * P.out_plane + (p & ~1ll);
-                            if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
-                        }
-                    } else {
-                        const int na = P.acc_mode == ACC_DECONV ? P.nacc : 1;
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t w = split_bf16(valid ? 0.25f * y[i] : 0.f);
+                        const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
+                        const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
+                        if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
+                        dst += P.out_plane;
+                    }
+                } else {
+                    const int na = P.acc_mode == ACC_DECONV ? P.nacc : 1;
 #pragma unroll 1
-                        for (int a = 0; a < na; ++a) {
-                            float v[16];
-                            tmem_ld16(t0 + (uint32_t)(a * P.acc_stride) + col0, v);
-                            const float* bs = sbias + a * P.N + col0;
-                            const long long pa = p + (long long)a * P.out_acc_stride;
-                            if (P.epi == EPI_LRELU_F32) {
+                    for (int a = 0; a < na; ++a) {
+                        float v[16];
+                        tmem_ld16(t0 + (uint32_t)(a * P.acc_stride) + col0, v);
+                        const float* bs = sbias + a * P.N + col0;
+                        const long long pa = p + (long long)a * P.out_acc_stride;
+                        if (P.epi == EPI_LRELU_F32) {
+                            if (valid) {
+                                float* o = P.out_f32 + (long long)col0 * P.out_plane + pa;
 #pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (valid && col0 + i < P.store_c1) P.out_f32[(long long)(col0 + i) * P.out_plane + pa] = lrelu(v[i] + bs[i], P.slope);
-                            } else {
+                                for (int i = 0; i < 16; ++i) { if (col0 + i < P.store_c1) *o = lrelu(v[i] + bs[i], P.slope); o += P.out_plane; }
+                            }
+                        } else {
+                            __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)col0 * P.out_plane + (pa & ~1ll);
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    const uint32_t w = split_bf16(valid ? lrelu(v[i] + bs[i], P.slope) : 0.f);
-                                    const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
-                                    const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
-                                    __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)(col0 + i) * P.out_plane + (pa & ~1ll);
-                                    if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
-                                }
+                            for (int i = 0; i < 16; ++i) {
+                                const uint32_t w = split_bf16(valid ? lrelu(v[i] + bs[i], P.slope) : 0.f);
+                                const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
+                                const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
+                                if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
+                                dst += P.out_plane;
                             }
                         }
                     }
-                }
-                if (P.epi == EPI_STATS_F32 && g < P.nstat) {
-                    const float ps = warp_sum(valid ? s1 : 0.f), pq = warp_sum(valid ? s2 : 0.f);
-                    const int cnt = __popc(__ballot_sync(0xffffffffu, valid)) * (nchunk * 16);
-                    if (lane == 0) {
-                        float4 r = red[ew * MAXG + g];
-                        r.x += (float)cnt; r.y += ps; r.z += pq; r.w = pilot;
-                        red[ew * MAXG + g] = r;
-                    }
-                    __syncwarp();
                 }
             }
             first_tile = false;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+            if (ew == 0 && lane == 0) V2_STAMP(7, (int)((tile - blockIdx.x) / gridDim.x));
             if (++as == P.acc_stages) { as = 0; aph ^= 1; }
         }
     } else if (GATED && warp >= GATE_WARP0) {
@@ -487,14 +534,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
-    if (P.epi == EPI_STATS_F32 && P.nstat > 0) {
-        for (int i = tid; i < NWARP_EPI * P.nstat; i += nthreads) {
-            const int ew = i / P.nstat, g = i % P.nstat;
-            P.sink.partial[(size_t)g * P.sink.stride + (size_t)blockIdx.x * NWARP_EPI + ew] = red[ew * MAXG + g];
+    if (P.dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); P.dbg[9 * 32 + 256 + blockIdx.x] = (long long)t_; }
+    if (P.epi == EPI_STATS_F32 && tid < P.nstat) {
+        // this CTA's partial of set `tid`: the 16 epilogue warps' sums re-referenced to one pilot (double, no divisions)
+        const int g = tid;
+        float k0 = 0.f; bool have = false;
+        for (int w = 0; w < NWARP_EPI; ++w) { const float4 r = red[w * MAXG + g]; if (!have && r.x > 0.f) { k0 = r.w; have = true; } }
+        double n = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int w = 0; w < NWARP_EPI; ++w) {
+            const float4 r = red[w * MAXG + g];
+            const double nb = (double)r.x, s1 = (double)r.y, s2 = (double)r.z, d = (double)r.w - (double)k0;
+            n += nb; a1 += s1 + nb * d; a2 += s2 + 2.0 * d * s1 + nb * d * d;
         }
+        P.sink.partial[(size_t)g * P.sink.stride + blockIdx.x] = make_float4((float)n, (float)a1, (float)a2, k0);
     }
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
-    if (P.epi == EPI_STATS_F32 && P.nstat > 0) stats2_finalize_last_cta(P.sink, NWARP_EPI * gridDim.x, gridDim.x, &P.aff);
+    if (P.epi == EPI_STATS_F32 && P.nstat > 0) stats2_finalize_last_cta(P.sink, gridDim.x, gridDim.x, &P.aff);
 }
 
 // ---- weight images: hi and lo bf16 parts of W^T, K-major rows of 128 bytes (64 channels), SWIZZLE_128B

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <string.h>
+#include <stdlib.h>
 #include "gemm_v2.cuh"
 
 namespace urnn {
@@ -33,6 +34,12 @@ static inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
+static inline CUtensorMapL2promotion l2promo() {
+    const char* e = getenv("URNN_V2_L2PROMO");
+    const int v = e ? atoi(e) : 256;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+}
+
 // tensor map over a split map: dims (pixels, channels, hi|lo), box (64 pixels, unit_ch channels, nhl), SWIZZLE_128B
 static inline int make_split_tmap(CUtensorMap* tm, const SplitMap& m, int unit_ch, int nhl) {
     EncodeTiledFn fn = encode_fn();
@@ -42,7 +49,7 @@ static inline int make_split_tmap(CUtensorMap* tm, const SplitMap& m, int unit_c
     cuuint32_t box[3] = {64, (cuuint32_t)unit_ch, (cuuint32_t)nhl};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, m.hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, l2promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for map C=%d ntot=%lld unit=%d", (int)r, m.C, m.ntot, unit_ch); return URNN_E_CUDA; }
     return URNN_OK;
 }
@@ -102,7 +109,9 @@ static inline int plan_gemm(GemmLaunch& L, int num_sms) {
         if (ns2 >= 4) { P.gdepth = 2; best = ns2; } else { P.gdepth = 1; best = pick(1); }
     }
     if (best < 2) { set_error("gemm_v2: weights %dx%d (hi+lo) leave no room for the operand ring", P.nrows, P.nkb * 64); return URNN_E_UNSUPPORTED; }
+    if (const char* e = getenv("URNN_V2_SLOTS")) { const int cap = atoi(e); if (cap >= 2 && cap < best) best = cap; }   // bring-up: ring depth cap
     P.nslots = best;
+    { const char* e = getenv("URNN_V2_L2AHEAD"); P.l2_ahead = e ? atoi(e) : 2; }
     L.smem = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total).total;
     const long long ntiles = P.ntot / TILE_M;
     L.grid = (int)(ntiles < num_sms ? ntiles : num_sms);
