@@ -43,6 +43,9 @@ extern "C" {
 
 /* arithmetic of the gate contractions */
 #define URNN_MATH_FP32 0       /* fp32 FFMA, fp32 accumulate: the parity mode (atol 1e-5 vs reference)                */
+#define URNN_MATH_F16X3 3     /* tcgen05 kind::f16 with every GEMM operand split into fp16 hi + lo (3 MMAs per K step: 22      */
+                               /* significant bits on both sides), fp32 accumulate / statistics / pre-norm maps; TMA-fed.     */
+                               /* Whole-step entry points only (ksize 1).  The mode that meets the T=180 tolerance.          */
 #define URNN_MATH_BF16 2       /* tcgen05 kind::f16: GEMM operands rounded to bf16, fp32 accumulate in TMEM, fp32     */
                                /* statistics / states; applies to the cell contractions and the stage stems (k=1)     */
 
@@ -188,6 +191,14 @@ int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float
  * double-buffered on internal streams and overlap the next step; the call returns after the last copy
  * has landed (it synchronises -- this is the one blocking entry point).  inputs_host / out_host should be
  * page-locked.  states[6] are device buffers updated in place across the T steps (ping-pong inside ws). */
+/* test.py:356-367 with DEVICE buffers: T steps, inputs_dev (T, Cin, H, W) and out_dev (T, H, W) resident in HBM, the six
+ * states (reference order, fp32 NCHW) updated in place.  Workspace: urnn_ed_sequence_dev_workspace_bytes.  Stream-ordered,
+ * no synchronisation.  prob_dev may be NULL; otherwise it receives the (T, H, W) wet probabilities. */
+size_t urnn_ed_sequence_dev_workspace_bytes(const urnn_ed_desc* d);
+int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T,
+                         const float* inputs_dev, float* out_dev, float* prob_dev, float* const* states,
+                         void* ws, size_t ws_bytes, void* stream);
+
 size_t urnn_ed_sequence_host_workspace_bytes(const urnn_ed_desc* d);
 int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T,
                           const float* inputs_host, float* out_host, float* const* states,

@@ -73,6 +73,7 @@ int urnn_cgru_fwd(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     tc_reset_direction();
 #endif
     switch (d->math) {
+        case URNN_MATH_F16X3:      // per-operator calls of the split mode run the fp32 FFMA kernels (same or better precision)
         case URNN_MATH_FP32: return cgru_fwd_fp32(d, p, x, e, h, h_out, ws, ws_bytes, st);
 #ifndef URNN_NO_TC
         case URNN_MATH_BF16: return cgru_fwd_bf16_standalone(d, p, x, 0, e, h, h_out, ws, ws_bytes, st);
@@ -209,6 +210,12 @@ static int ed_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, EdPlan* pl)
 }
 
 size_t urnn_ed_step_workspace_bytes(const urnn_ed_desc* d) {
+#ifndef URNN_NO_TC
+    if (d && d->math == URNN_MATH_F16X3) {
+        if (d->H <= 0 || d->W <= 0 || d->H % 4 || d->W % 4) { set_error("ed: H=%d W=%d must be positive multiples of 4", d->H, d->W); return 0; }
+        return v2_step_workspace_bytes(d) + (size_t)2 * d->H * d->W * sizeof(float) + 256;
+    }
+#endif
     EdPlan pl;
     if (ed_plan(d, nullptr, 0, &pl) != URNN_OK) return 0;
     return pl.total;
@@ -222,6 +229,13 @@ struct Stem1 { const float* x; int cin; const float* w; long w_ld; const float* 
 static int ed_step_impl(const urnn_ed_desc* d, const urnn_ed_params* p, const Stem1& s1,
                         const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes,
                         void* stream) {
+    URNN_CHECK_ARG(d && p && s1.x && sin && sout && out, "ed_step: null pointer");
+#ifndef URNN_NO_TC
+    if (d->math == URNN_MATH_F16X3) {
+        for (int i = 0; i < 6; ++i) URNN_CHECK_ARG(sin[i] && sout[i], "ed_step: state %d null", i);
+        return v2_step_fwd_nchw(d, p, s1.x, s1.cin, s1.w, s1.w_ld, s1.b, sin, sout, out, ws, ws_bytes, (cudaStream_t)stream);
+    }
+#endif
     EdPlan pl;
     URNN_TRY(ed_plan(d, ws, ws_bytes, &pl));
     const float* input = s1.x;
@@ -298,6 +312,9 @@ static int ed_step_impl(const urnn_ed_desc* d, const urnn_ed_params* p, const St
 
 // ------------------------------------------------------------------------------------------------ host-buffer sequence
 // test.py:356-375 with host buffers: H2D of step t+1's input and D2H of step t-1's depth map overlap step t.
+// frees a sequence context on every exit path
+struct SeqGuard { V2Seq* seq = nullptr; ~SeqGuard() { if (seq) v2_seq_end(seq, 0, nullptr, nullptr); } };
+
 struct SeqPlan {
     float* in[2]; float* out[2]; float* st[2][6]; void* step_ws; size_t step_ws_bytes; size_t total;
     size_t state_elems[6];
@@ -315,8 +332,9 @@ static int seq_plan(const urnn_ed_desc* d, void* ws, size_t ws_bytes, SeqPlan* s
         sp->st[0][k] = nullptr;                                   // ping buffer = the caller's state buffer
         sp->st[1][k] = a.take<float>(sp->state_elems[k]);
     }
-    sp->step_ws_bytes = pl.total;
-    sp->step_ws = a.take<char>(pl.total);
+    sp->step_ws_bytes = urnn_ed_step_workspace_bytes(d);
+    if (sp->step_ws_bytes == 0) return URNN_E_INVALID;
+    sp->step_ws = a.take<char>(sp->step_ws_bytes);
     sp->total = align_up(a.off, 256);
     return URNN_OK;
 }
@@ -363,6 +381,15 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
     URNN_CUDA(cudaStreamWaitEvent(s_out, ev_free[0], 0));
     URNN_CUDA(cudaMemcpyAsync(sp.in[0], inputs_host, in_elems * sizeof(float), cudaMemcpyHostToDevice, s_in));
     URNN_CUDA(cudaEventRecord(ev_in[0], s_in));
+    // URNN_MATH_F16X3: the states stay in the internal split layout for the whole sequence
+    SeqGuard sg; V2Seq*& seq = sg.seq;
+#ifndef URNN_NO_TC
+    if (d->math == URNN_MATH_F16X3) {
+        int rc = URNN_OK;
+        seq = v2_seq_begin(d, p, states, sp.step_ws, sp.step_ws_bytes, st, &rc);
+        if (!seq) return rc;
+    }
+#endif
     for (int t = 0; t < T; ++t) {
         const int b = t & 1;
         if (t + 1 < T) {                                    // prefetch the next input into the other buffer
@@ -375,18 +402,64 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
         if (t >= 2) URNN_CUDA(cudaStreamWaitEvent(st, ev_out[b], 0));             // out[b] has been drained to the host
         const float* sin[6]; float* sout[6];
         for (int k = 0; k < 6; ++k) { sin[k] = sp.st[b][k]; sout[k] = sp.st[b ^ 1][k]; }
-        URNN_TRY(urnn_ed_step_fwd(d, p, sp.in[b], sin, sout, sp.out[b], sp.step_ws, sp.step_ws_bytes, stream));
+        if (seq) URNN_TRY(v2_seq_step(seq, t, sp.in[b], d->Cin, p->enc_stem_w[0], (long long)d->Cin, p->enc_stem_b[0], sp.out[b], st));
+        else URNN_TRY(urnn_ed_step_fwd(d, p, sp.in[b], sin, sout, sp.out[b], sp.step_ws, sp.step_ws_bytes, stream));
         URNN_CUDA(cudaEventRecord(ev_step[b], st));
         URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
         URNN_CUDA(cudaMemcpyAsync(out_host + (size_t)t * N, sp.out[b], N * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         URNN_CUDA(cudaEventRecord(ev_out[b], s_out));
     }
-    if (T & 1) {                                            // final states live in the workspace buffers: copy back
+    if (seq) { V2Seq* q = seq; seq = nullptr; URNN_TRY(v2_seq_end(q, T, states, st)); }
+    else if (T & 1) {                                       // final states live in the workspace buffers: copy back
         for (int k = 0; k < 6; ++k)
             URNN_CUDA(cudaMemcpyAsync(sp.st[0][k], sp.st[1][k], sp.state_elems[k] * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     URNN_CUDA(cudaStreamSynchronize(s_out));
     URNN_CUDA(cudaStreamSynchronize(st));
+    return URNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device-buffer sequence
+size_t urnn_ed_sequence_dev_workspace_bytes(const urnn_ed_desc* d) {
+    SeqPlan sp;
+    if (seq_plan(d, nullptr, 0, &sp) != URNN_OK) return 0;
+    return sp.total;
+}
+
+int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T, const float* inputs_dev, float* out_dev,
+                         float* prob_dev, float* const* states, void* ws, size_t ws_bytes, void* stream) {
+    URNN_CHECK_ARG(d && p && inputs_dev && out_dev && states && T > 0, "ed_sequence_dev: bad argument");
+    SeqPlan sp;
+    URNN_TRY(seq_plan(d, ws, ws_bytes, &sp));
+    if (sp.total > ws_bytes) { set_error("ed_sequence_dev: workspace %zu < %zu bytes", ws_bytes, sp.total); return URNN_E_WORKSPACE; }
+    for (int k = 0; k < 6; ++k) { URNN_CHECK_ARG(states[k], "ed_sequence_dev: null state %d", k); sp.st[0][k] = states[k]; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)d->H * d->W, in_elems = (size_t)d->Cin * N;
+    SeqGuard sg; V2Seq*& seq = sg.seq;
+#ifndef URNN_NO_TC
+    if (d->math == URNN_MATH_F16X3) {
+        int rc = URNN_OK;
+        seq = v2_seq_begin(d, p, states, sp.step_ws, sp.step_ws_bytes, st, &rc);
+        if (!seq) return rc;
+    }
+#endif
+    for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        const float* x = inputs_dev + (size_t)t * in_elems;
+        if (seq) URNN_TRY(v2_seq_step(seq, t, x, d->Cin, p->enc_stem_w[0], (long long)d->Cin, p->enc_stem_b[0], sp.out[0], st));
+        else {
+            const float* sin[6]; float* sout[6];
+            for (int k = 0; k < 6; ++k) { sin[k] = sp.st[b][k]; sout[k] = sp.st[b ^ 1][k]; }
+            URNN_TRY(urnn_ed_step_fwd(d, p, x, sin, sout, sp.out[0], sp.step_ws, sp.step_ws_bytes, stream));
+        }
+        URNN_CUDA(cudaMemcpyAsync(out_dev + (size_t)t * N, sp.out[0], N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (prob_dev) URNN_CUDA(cudaMemcpyAsync(prob_dev + (size_t)t * N, sp.out[0] + N, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (seq) { V2Seq* q = seq; seq = nullptr; URNN_TRY(v2_seq_end(q, T, states, st)); }
+    else if (T & 1) {
+        for (int k = 0; k < 6; ++k)
+            URNN_CUDA(cudaMemcpyAsync(sp.st[0][k], sp.st[1][k], sp.state_elems[k] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
     return URNN_OK;
 }
 
@@ -434,8 +507,9 @@ static int event_plan(const urnn_ed_desc* d, const urnn_event_desc* ev, void* ws
     ep->bias_all = a.take<float>((size_t)ev->T * d->enc_conv[0]);
     for (int i = 0; i < 2; ++i) ep->out[i] = a.take<float>(2 * N);
     for (int k = 0; k < 6; ++k) { ep->state_elems[k] = (size_t)ch[k] * (N >> (2 * sc[k])); ep->st[k] = a.take<float>(ep->state_elems[k]); }
-    ep->step_ws_bytes = pl.total;
-    ep->step_ws = a.take<char>(pl.total);
+    ep->step_ws_bytes = urnn_ed_step_workspace_bytes(d);
+    if (ep->step_ws_bytes == 0) return URNN_E_INVALID;
+    ep->step_ws = a.take<char>(ep->step_ws_bytes);
     ep->total = align_up(a.off, 256);
     return URNN_OK;
 }
@@ -482,6 +556,14 @@ int urnn_ed_event_host(const urnn_ed_desc* d, const urnn_ed_params* p, const urn
     URNN_LAUNCH_CHECK();
     URNN_CUDA(cudaEventRecord(ev_start, st));
     URNN_CUDA(cudaStreamWaitEvent(s_out, ev_start, 0));
+    SeqGuard sg; V2Seq*& seq = sg.seq;
+#ifndef URNN_NO_TC
+    if (d->math == URNN_MATH_F16X3) {
+        int rc = URNN_OK;
+        seq = v2_seq_begin(d, p, states, ep.step_ws, ep.step_ws_bytes, st, &rc);
+        if (!seq) return rc;
+    }
+#endif
     // ---- T steps, states ping-pong between the caller's buffers and the workspace
     for (int t = 0; t < T; ++t) {
         const int b = t & 1;
@@ -489,13 +571,15 @@ int urnn_ed_event_host(const urnn_ed_desc* d, const urnn_ed_params* p, const urn
         const float* sin[6]; float* sout[6];
         for (int k = 0; k < 6; ++k) { sin[k] = b ? ep.st[k] : states[k]; sout[k] = b ? states[k] : ep.st[k]; }
         Stem1 s1{ep.maps, 3, p->enc_stem_w[0] + 2 * ev->hist, (long)d->Cin, ep.bias_all + (size_t)t * cout0};
-        URNN_TRY(ed_step_impl(d, p, s1, sin, sout, ep.out[b], ep.step_ws, ep.step_ws_bytes, stream));
+        if (seq) URNN_TRY(v2_seq_step(seq, t, s1.x, s1.cin, s1.w, s1.w_ld, s1.b, ep.out[b], st));
+        else URNN_TRY(ed_step_impl(d, p, s1, sin, sout, ep.out[b], ep.step_ws, ep.step_ws_bytes, stream));
         URNN_CUDA(cudaEventRecord(ev_step[b], st));
         URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
         URNN_CUDA(cudaMemcpyAsync(out_host + (size_t)t * N, ep.out[b], N * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         URNN_CUDA(cudaEventRecord(ev_out[b], s_out));
     }
-    if (T & 1) {
+    if (seq) { V2Seq* q = seq; seq = nullptr; URNN_TRY(v2_seq_end(q, T, states, st)); }
+    else if (T & 1) {
         for (int k = 0; k < 6; ++k)
             URNN_CUDA(cudaMemcpyAsync(states[k], ep.st[k], ep.state_elems[k] * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }

@@ -25,12 +25,13 @@ namespace v2 {
 using namespace ptx;
 
 constexpr int TILE_M = 128;
-constexpr int SLOT_BYTES = 16384;         // one ring slot: 32 channels x 128 pixels x {hi,lo} bf16
+constexpr int SLOT_BYTES = 16384;         // one ring slot: 32 channels x 128 pixels x {hi,lo} 16-bit
 constexpr int MAX_STEPS = 16;
 constexpr int MAXG = 8;                   // 32-column groups per accumulator (N <= 256)
-constexpr int NWARP_EPI = 16;
-constexpr int EPI_WARP0 = 4, GATE_WARP0 = 20;
-constexpr int NTHREADS_PLAIN = 32 * GATE_WARP0, NTHREADS_GATED = 32 * (GATE_WARP0 + 4);
+constexpr int NWARP_EPI = 16;                 // plain launches: 16 epilogue warps; gated launches: 8 epilogue + 12 gate warps
+constexpr int NWARP_EPI_GATED = 8, NWARP_GATE = 12;
+constexpr int EPI_WARP0 = 4;
+constexpr int NTHREADS_PLAIN = 32 * (EPI_WARP0 + NWARP_EPI), NTHREADS_GATED = 32 * (EPI_WARP0 + NWARP_EPI_GATED + NWARP_GATE);
 constexpr size_t SMEM_MAX = 231424;       // 227 KB opt-in limit minus 1 KB for static shared memory
 
 enum { EPI_STATS_F32 = 0, EPI_LRELU_SPLIT = 1, EPI_LRELU_F32 = 2 };
@@ -107,10 +108,12 @@ __device__ __forceinline__ void stats2_finalize_last_cta(const StatSink2& s, int
     // in a fixed order: lane-strided, then a fixed shuffle tree.
     const int nwarp = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int set = warp; set < s.nsets; set += nwarp) {
-        const double k00 = (double)__ldcg(&s.partial[(size_t)set * s.stride]).w;
+        double k00 = 0.0;
+        for (int i = 0; i < ncontrib; ++i) { const float4 v = __ldcg(&s.partial[(size_t)set * s.stride + i]); if (v.x > 0.f) { k00 = (double)v.w; break; } }
         double n = 0.0, a1 = 0.0, a2 = 0.0;
         for (int i = lane; i < ncontrib; i += 32) {
             const float4 v = __ldcg(&s.partial[(size_t)set * s.stride + i]);
+            if (!(v.x > 0.f)) continue;              // empty partial (all-padding CTA): its pilot may be garbage
             const double nb = (double)v.x, s1 = (double)v.y, s2 = (double)v.z, d = (double)v.w - k00;
             n += nb; a1 += s1 + nb * d; a2 += s2 + 2.0 * d * s1 + nb * d * d;
         }
@@ -157,14 +160,14 @@ struct GemmParams {
     // reset-gated operand segment (candidate GEMM): r*h with r = sigmoid(gate_pre*scale + shift), produced by the gate warps
     int gate_ch;                                   // 0: none, else F (multiple of 32)
     int gate_k0;                                   // position of the gated channels in the weight image's K axis
-    const __nv_bfloat16* gate_h; long long gate_h_plane, gate_h_lo;    // split map of h: hi planes, lo planes gate_h_lo elements further
+    const sp16* gate_h; long long gate_h_plane, gate_h_lo;    // split map of h: hi planes, lo planes gate_h_lo elements further
     const float* gate_pre; long long gate_pre_plane;                   // fp32 pre-GroupNorm reset-gate map [F][plane]
     const float* gate_scale; const float* gate_shift;                  // folded GroupNorm affine of those F channels
     int gdepth;                                    // gated-operand buffers (1 or 2)
     // weights: resident image, hi then lo, each nkb blocks of (nrows x 128 B) (64 channels, K-major, SWIZZLE_128B)
     const void* wimg; int nkb, nrows;
     int N;                                         // columns per accumulator (multiple of 16, <= 256)
-    int nmma;                                      // 3: hi/lo split product; 1: single bf16 pass
+    int nmma;                                      // 3: hi/lo split product; 1: single pass (hi parts only)
     // pixels: tiles cover [0, ntot); pixel p is real iff (p % blk_stride) < blk_valid
     long long ntot, blk_stride, blk_valid;
     // epilogue
@@ -172,7 +175,8 @@ struct GemmParams {
     const float* bias; int nbias, bias_mod;        // bias[col % bias_mod] for col < nbias
     float* out_f32; long long out_plane;           // fp32 planes out_f32[col*out_plane + p]
     int store_c0, store_c1;                        // EPI_STATS_F32: columns [store_c0, store_c1) are stored
-    __nv_bfloat16* out_hi; long long out_lo;       // split map destination: hi planes, lo planes out_lo elements further
+    sp16* out_hi; long long out_lo;       // split map destination: hi planes, lo planes out_lo elements further
+    int nchw, nchw_w, nchw_w4; long long nchw_n4p;  // EPI_LRELU_F32: destination is an NCHW image (un-permute the phase-separated layout)
     long long out_acc_stride;                      // ACC_DECONV: pixel offset between the destination blocks of the accumulators
     int nstat; StatSink2 sink; AffineOut aff;      // leading 32-column groups with GroupNorm statistics
     int l2_ahead;                                  // tiles of L2 prefetch distance (0: off)
@@ -214,6 +218,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);          // provably warp-uniform (uniform registers for TMEM / MMA operands)
     const int nthreads = GATED ? NTHREADS_GATED : NTHREADS_PLAIN;
+    constexpr int NWE = GATED ? NWARP_EPI_GATED : NWARP_EPI;      // epilogue warps of this instantiation
+    constexpr int GATE_WARP0 = EPI_WARP0 + NWE;
     const int ncols_total = P.acc_mode == ACC_DECONV ? P.nacc * P.N : P.N;
     const SmemPlan L = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total);
     // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | gfull[2] | gempty[2] | tmem slot
@@ -229,8 +235,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     if (tid == 0) {
         for (int s = 0; s < P.nslots; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NWARP_EPI);
-            mbar_init(gfull0 + 8 * a, 4); mbar_init(gempty0 + 8 * a, 1);
+            mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NWE);
+            mbar_init(gfull0 + 8 * a, NWARP_GATE); mbar_init(gempty0 + 8 * a, 1);
         }
         fence_barrier_init();
     }
@@ -265,7 +271,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     // from here on the previous kernel's outputs are consumed
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if constexpr (GATED) {
-        for (int i = tid; i < P.gate_ch; i += nthreads) { sgaff[2 * i] = __ldg(P.gate_scale + i); sgaff[2 * i + 1] = __ldg(P.gate_shift + i); }
+        for (int i = tid; i < P.gate_ch; i += nthreads) { sgaff[2 * i] = -1.4426950408889634f * __ldg(P.gate_scale + i); sgaff[2 * i + 1] = -1.4426950408889634f * __ldg(P.gate_shift + i); }
         __syncthreads();
     }
 #define V2_STAMP(ev, ti) do { if (P.dbg && blockIdx.x == 0 && lane == 0 && (ti) < 32) P.dbg[(ev) * 32 + (ti)] = clock64(); } while (0)
@@ -302,7 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         // =========================================================================== MMA issuer
         // The whole warp walks the pipeline with warp-uniform values (descriptors live in uniform registers); one elected
         // lane issues tcgen05.mma / tcgen05.commit.
-        const uint32_t idesc = instr_desc_bf16(P.N);
+        const uint32_t idesc = instr_desc_16(P.N, SPLIT_FMT);
         int slot = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0; int gd = 0; uint32_t gph = 0;
         const uint32_t hl = P.nmma == 3 ? 2u : 1u;
         const uint32_t wlo16 = wlo >> 4;
@@ -381,7 +387,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         const int row = lq * 32 + lane;
         const int nchunks = P.N >> 4;
         const unsigned tiles_per_blk = (unsigned)(P.blk_stride / TILE_M);
-        int as = 0; uint32_t aph = 0; bool first_tile = true;
+        int as = 0; uint32_t aph = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long p = tile * TILE_M + row;
             const unsigned in_blk = ((unsigned)tile % tiles_per_blk) * TILE_M + row;
@@ -392,7 +398,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
             if (ew == 0 && lane == 0) V2_STAMP(6, (int)((tile - blockIdx.x) / gridDim.x));
             const uint32_t t0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(as * P.nacc * P.acc_stride);
 #pragma unroll 1
-            for (int c = qtr; c < nchunks; c += 4) {
+            for (int c = qtr; c < nchunks; c += NWE / 4) {
                 const int col0 = c * 16;
                 if (P.epi == EPI_STATS_F32) {
                     float v[16];
@@ -403,7 +409,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
                     for (int i = 0; i < 4; ++i) { const float4 b = bs4[i]; bsv[4 * i] = b.x; bsv[4 * i + 1] = b.y; bsv[4 * i + 2] = b.z; bsv[4 * i + 3] = b.w; }
                     const int g = c >> 1;
                     float pilot = 0.f;
-                    if (g < P.nstat) pilot = first_tile ? __shfl_sync(0xffffffffu, v[0] + bsv[0], 0) : red[ew * MAXG + g].w;
+                    if (g < P.nstat) {                       // this warp's pilot for the group: its first real value
+                        const float4 r = red[ew * MAXG + g];
+                        pilot = r.x > 0.f ? r.w : __shfl_sync(0xffffffffu, v[0] + bsv[0], 0);
+                    }
                     float y[16], s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -419,7 +428,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
                     if (g < P.nstat) {
                         const float ps = warp_sum(valid ? s1 : 0.f), pq = warp_sum(valid ? s2 : 0.f);
                         const int cnt = __popc(__ballot_sync(0xffffffffu, valid)) * 16;
-                        if (lane == 0) {
+                        if (lane == 0 && cnt > 0) {
                             float4 r = red[ew * MAXG + g];
                             r.x += (float)cnt; r.y += ps; r.z += pq; r.w = pilot;
                             red[ew * MAXG + g] = r;
@@ -439,10 +448,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
 #pragma unroll
                         for (int i = 0; i < 16; ++i) y[i] += lrelu(v[i] + bs[i], P.slope);
                     }
-                    __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)col0 * P.out_plane + (p & ~1ll);
+                    sp16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)col0 * P.out_plane + (p & ~1ll);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const uint32_t w = split_bf16(valid ? 0.25f * y[i] : 0.f);
+                        const uint32_t w = split16(valid ? 0.25f * y[i] : 0.f);
                         const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
                         const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
                         if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
@@ -458,15 +467,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
                         const long long pa = p + (long long)a * P.out_acc_stride;
                         if (P.epi == EPI_LRELU_F32) {
                             if (valid) {
-                                float* o = P.out_f32 + (long long)col0 * P.out_plane + pa;
+                                long long po = pa;
+                                if (P.nchw) {
+                                    const unsigned blk = (unsigned)(p / P.nchw_n4p), q = (unsigned)(p - (long long)blk * P.nchw_n4p);
+                                    const unsigned qy = q / (unsigned)P.nchw_w4, qx = q - qy * (unsigned)P.nchw_w4, f1 = blk >> 2, f2 = blk & 3;
+                                    po = (long long)(4 * qy + 2 * (f2 >> 1) + (f1 >> 1)) * P.nchw_w + (4 * qx + 2 * (f2 & 1) + (f1 & 1));
+                                }
+                                float* o = P.out_f32 + (long long)col0 * P.out_plane + po;
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) { if (col0 + i < P.store_c1) *o = lrelu(v[i] + bs[i], P.slope); o += P.out_plane; }
                             }
                         } else {
-                            __nv_bfloat16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)col0 * P.out_plane + (pa & ~1ll);
+                            sp16* dst = P.out_hi + ((lane & 1) ? P.out_lo : 0) + (long long)col0 * P.out_plane + (pa & ~1ll);
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
-                                const uint32_t w = split_bf16(valid ? lrelu(v[i] + bs[i], P.slope) : 0.f);
+                                const uint32_t w = split16(valid ? lrelu(v[i] + bs[i], P.slope) : 0.f);
                                 const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
                                 const uint32_t pk = (lane & 1) ? ((o >> 16) | (w & 0xFFFF0000u)) : ((w & 0xFFFFu) | (o << 16));
                                 if (pair_valid) *reinterpret_cast<uint32_t*>(dst) = pk;
@@ -476,7 +491,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
                     }
                 }
             }
-            first_tile = false;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * as);
@@ -485,45 +499,52 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         }
     } else if (GATED && warp >= GATE_WARP0) {
         // =========================================================================== gate warps: r*h -> hi/lo operand
-        // task = one 16-byte piece (8 pixels of one channel): lanes cover 2 channel rows x 16 pieces (coalesced 256 B rows)
+        // task = one 16-byte piece (8 pixels of one channel): lanes cover 2 channel rows x 16 pieces (coalesced 256 B rows);
+        // 12 warps, two tasks in flight per thread.  sigmoid(a*g + b) = 1 / (1 + 2^(-(a*g+b)*log2 e)): the affine is folded.
         const int gt = tid - GATE_WARP0 * 32;
-        const int ntask = P.gate_ch * 16 / 128;
+        constexpr int NGT = NWARP_GATE * 32;
+        const int ntask = P.gate_ch * 16;
         int gd = 0; uint32_t gph = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long p0 = tile * TILE_M;
             mbar_wait(gempty0 + 8 * gd, gph ^ 1);
             uint8_t* gb = sm + L.gbuf_off + (size_t)gd * (P.gate_ch / 32) * SLOT_BYTES;
 #pragma unroll 1
-            for (int t0 = 0; t0 < ntask; t0 += 4) {
-                uint4 hi[4], lo[4]; float4 g0[4], g1[4];
+            for (int t0 = gt; t0 < ntask; t0 += 2 * NGT) {
+                uint4 hi[2], lo[2]; float4 g0[2], g1[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int idx = (t0 + q) * 128 + gt, ch = idx >> 4, j = idx & 15;
-                    const long long e = (long long)ch * P.gate_h_plane + p0 + 8 * j;
-                    hi[q] = __ldg(reinterpret_cast<const uint4*>(P.gate_h + e));
-                    lo[q] = __ldg(reinterpret_cast<const uint4*>(P.gate_h + P.gate_h_lo + e));
-                    const float4* gp = reinterpret_cast<const float4*>(P.gate_pre + (long long)ch * P.gate_pre_plane + p0 + 8 * j);
-                    g0[q] = __ldg(gp); g1[q] = __ldg(gp + 1);
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = t0 + q * NGT;
+                    if (idx < ntask) {
+                        const int ch = idx >> 4, j = idx & 15;
+                        const long long e = (long long)ch * P.gate_h_plane + p0 + 8 * j;
+                        hi[q] = __ldg(reinterpret_cast<const uint4*>(P.gate_h + e));
+                        lo[q] = __ldg(reinterpret_cast<const uint4*>(P.gate_h + P.gate_h_lo + e));
+                        const float4* gp = reinterpret_cast<const float4*>(P.gate_pre + (long long)ch * P.gate_pre_plane + p0 + 8 * j);
+                        g0[q] = __ldg(gp); g1[q] = __ldg(gp + 1);
+                    }
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int idx = (t0 + q) * 128 + gt, ch = idx >> 4, j = idx & 15;
-                    const float sc = sgaff[2 * ch], sh = sgaff[2 * ch + 1];
-                    const uint32_t hw[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w}, lw[4] = {lo[q].x, lo[q].y, lo[q].z, lo[q].w};
-                    const float gv[8] = {g0[q].x, g0[q].y, g0[q].z, g0[q].w, g1[q].x, g1[q].y, g1[q].z, g1[q].w};
-                    uint32_t oh[4], ol[4];
+                for (int q = 0; q < 2; ++q) {
+                    const int idx = t0 + q * NGT;
+                    if (idx < ntask) {
+                        const int ch = idx >> 4, j = idx & 15;
+                        const float sc = sgaff[2 * ch], sh = sgaff[2 * ch + 1];          // pre-multiplied by -log2(e)
+                        const uint32_t hw[4] = {hi[q].x, hi[q].y, hi[q].z, hi[q].w}, lw[4] = {lo[q].x, lo[q].y, lo[q].z, lo[q].w};
+                        const float gv[8] = {g0[q].x, g0[q].y, g0[q].z, g0[q].w, g1[q].x, g1[q].y, g1[q].z, g1[q].w};
+                        uint32_t oh[4], ol[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float h0 = bf16lo_to_f32(hw[u]) + bf16lo_to_f32(lw[u]), h1 = bf16hi_to_f32(hw[u]) + bf16hi_to_f32(lw[u]);
-                        const uint32_t w0 = split_bf16(h0 * sigmoid_fast(fmaf(gv[2 * u], sc, sh)));
-                        const uint32_t w1 = split_bf16(h1 * sigmoid_fast(fmaf(gv[2 * u + 1], sc, sh)));
-                        oh[u] = (w0 & 0xFFFFu) | (w1 << 16);
-                        ol[u] = (w0 >> 16) | (w1 & 0xFFFF0000u);
+                        for (int u = 0; u < 4; ++u) {
+                            const float h0 = lo16_to_f32(hw[u]) + lo16_to_f32(lw[u]), h1 = hi16_to_f32(hw[u]) + hi16_to_f32(lw[u]);
+                            const float v0 = __fdividef(h0, 1.0f + ex2_approx(fmaf(gv[2 * u], sc, sh)));
+                            const float v1 = __fdividef(h1, 1.0f + ex2_approx(fmaf(gv[2 * u + 1], sc, sh)));
+                            split16x2(v0, v1, oh[u], ol[u]);
+                        }
+                        const int cu = ch & 31;
+                        uint8_t* d = gb + (size_t)(ch >> 5) * SLOT_BYTES + (j >> 3) * 8192 + cu * 128 + (((j & 7) ^ (cu & 7)) << 4);
+                        *reinterpret_cast<uint4*>(d) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                        *reinterpret_cast<uint4*>(d + 4096) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                     }
-                    const int cu = ch & 31;
-                    uint8_t* d = gb + (size_t)(ch >> 5) * SLOT_BYTES + (j >> 3) * 8192 + cu * 128 + (((j & 7) ^ (cu & 7)) << 4);
-                    *reinterpret_cast<uint4*>(d) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-                    *reinterpret_cast<uint4*>(d + 4096) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                 }
             }
             fence_proxy_async();
@@ -539,14 +560,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         // this CTA's partial of set `tid`: the 16 epilogue warps' sums re-referenced to one pilot (double, no divisions)
         const int g = tid;
         float k0 = 0.f; bool have = false;
-        for (int w = 0; w < NWARP_EPI; ++w) { const float4 r = red[w * MAXG + g]; if (!have && r.x > 0.f) { k0 = r.w; have = true; } }
+        for (int w = 0; w < NWE; ++w) { const float4 r = red[w * MAXG + g]; if (!have && r.x > 0.f) { k0 = r.w; have = true; } }
         double n = 0.0, a1 = 0.0, a2 = 0.0;
-        for (int w = 0; w < NWARP_EPI; ++w) {
+        for (int w = 0; w < NWE; ++w) {
             const float4 r = red[w * MAXG + g];
+            if (!(r.x > 0.f)) continue;              // warps that only saw padding pixels: pilot may be garbage
             const double nb = (double)r.x, s1 = (double)r.y, s2 = (double)r.z, d = (double)r.w - (double)k0;
             n += nb; a1 += s1 + nb * d; a2 += s2 + 2.0 * d * s1 + nb * d * d;
         }
-        P.sink.partial[(size_t)g * P.sink.stride + blockIdx.x] = make_float4((float)n, (float)a1, (float)a2, k0);
+        P.sink.partial[(size_t)g * P.sink.stride + blockIdx.x] = have ? make_float4((float)n, (float)a1, (float)a2, k0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
     if (P.epi == EPI_STATS_F32 && P.nstat > 0) stats2_finalize_last_cta(P.sink, gridDim.x, gridDim.x, &P.aff);
@@ -581,7 +603,7 @@ __global__ void __launch_bounds__(256) wimg_kernel(const WImgBatch B) {
                 v[e] = (k < S.K && n < S.nrows_valid)
                            ? __ldg(S.W + (long long)(n % S.racc) * S.w_ld + (long long)(n / S.racc) * S.w_acc + (long long)(k + S.k_skip) * S.w_ks) : 0.f;
             }
-            const uint32_t w0 = split_bf16(v[0]), w1 = split_bf16(v[1]);
+            const uint32_t w0 = split16(v[0]), w1 = split16(v[1]);
             h[u] = (w0 & 0xFFFFu) | (w1 << 16);
             l[u] = (w0 >> 16) | (w1 & 0xFFFF0000u);
         }

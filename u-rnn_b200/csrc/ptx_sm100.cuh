@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace urnn {
@@ -119,19 +120,44 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t 
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D fp32, A bf16 MN-major, B bf16 K-major, M=128, N=nout
-__device__ __forceinline__ uint32_t instr_desc_bf16(int nout) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(nout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A MN-major, B K-major, M=128, N=nout; both operands fp16 (format 0) or bf16 (1)
+__device__ __forceinline__ uint32_t instr_desc_16(int nout, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | ((uint32_t)(nout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// ---- bf16 hi/lo split: v = hi + lo + O(2^-18 |v|)
-__device__ __forceinline__ uint32_t split_bf16(float v) {          // low half: hi, high half: lo
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-    return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// ---- hi/lo split of an fp32 value into two 16-bit floats: v = hi + lo.
+// fp16 pairs (default): 11 + 11 significant bits -- fp32-grade products with three MMAs (the dropped lo*lo term is 2^-24);
+// values beyond +-65504 saturate.  bf16 pairs (URNN_SPLIT_BF16): 8 + 8 bits, fp32 range, error 2^-18 per operand --
+// measured to leave the config-3 max |d state| budget at T = 180 on the full grid (0.35 vs 0.1).
+#ifdef URNN_SPLIT_BF16
+typedef __nv_bfloat16 sp16;
+constexpr uint32_t SPLIT_FMT = 1;
+__device__ __forceinline__ float lo16_to_f32(uint32_t w) { return __uint_as_float(w << 16); }              // low 16-bit element of a pair
+__device__ __forceinline__ float hi16_to_f32(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }      // high 16-bit element
+__device__ __forceinline__ uint32_t pack2_16(float a, float b) { const __nv_bfloat162 t = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&t); }
+#else
+typedef __half sp16;
+constexpr uint32_t SPLIT_FMT = 0;
+__device__ __forceinline__ float lo16_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float hi16_to_f32(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+__device__ __forceinline__ uint32_t pack2_16(float a, float b) {
+    const __half2 t = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<const uint32_t*>(&t);
 }
-__device__ __forceinline__ float bf16lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf16hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+#endif
+// split one value: low half of the result = hi part, high half = lo part
+__device__ __forceinline__ uint32_t split16(float v) {
+    const uint32_t h = pack2_16(v, 0.f) & 0xFFFFu;
+    const uint32_t l = pack2_16(v - lo16_to_f32(h), 0.f) & 0xFFFFu;
+    return h | (l << 16);
+}
+// split a pixel pair: (hi pair, lo pair), each packed (first pixel in the low half)
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack2_16(a, b);
+    lo = pack2_16(a - lo16_to_f32(hi), b - hi16_to_f32(hi));
+}
 
 }  // namespace ptx
 }  // namespace urnn

@@ -45,6 +45,16 @@ int conv1x1_lrelu_fwd_tc(int Cin, int Cout, int H, int W, int pool, float slope,
 int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const void* x, int xkind, const float* w,
                            const float* b, __nv_bfloat16* y_bf16, float* y_f32, cudaStream_t st, long y_plane = 0);
 
+// URNN_MATH_F16X3 (urnn_v2.cu): the step on the second-generation pixel GEMM; states stay in the internal split layout
+// between the steps of a sequence
+struct V2Seq;
+size_t v2_step_workspace_bytes(const urnn_ed_desc* d);
+int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float* x, int cin, const float* w, long long w_ld, const float* b,
+                     const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc);
+int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st);
+int v2_seq_end(V2Seq* s, int T, float* const* states, cudaStream_t st);
+
 // fp32 FFMA path (urnn_fp32.cu)
 int cgru_fwd_fp32_passes(const urnn_cell_desc* d, const urnn_cell_params* p, const float* x, const float* e,
                          const float* h, CellWsView* wout, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -1,0 +1,570 @@
+// urnn_v2.cu -- URNN_MATH_F16X3: the encoder-decoder time step on the second-generation tcgen05 pixel GEMM (gemm_v2.cuh).
+//
+// Arithmetic: every GEMM operand is an fp16 hi + lo pair (22 significant bits on both sides, three MMAs per K=16 step),
+// accumulation / GroupNorm / LayerNorm statistics / gates / blend in fp32, pre-norm maps stored as fp32.  This is the mode
+// that stays inside the config-3 tolerance at T = 180 (tests/test_gpu_x3.py); single-pass bf16 does not, and bf16 hi+lo pairs miss the max |d state| bound on the full grid.
+//
+// Internal data layout ("phase-separated"): an H x W map (H, W multiples of 4) is stored as 16
+// blocks (full resolution), 4 blocks (half) or 1 block (quarter) of n4p = roundup((H/4)*(W/4), 128) pixels:
+//     full-res (y, x)  ->  block ((y&1)*2 + (x&1))*4 + (((y>>1)&1)*2 + ((x>>1)&1)),  position (y>>2)*(W/4) + (x>>2)
+// so that the 2x2 children of a coarse pixel sit at the SAME position of four consecutive block groups:
+// AvgPool2 (utils.py:92-94) and ConvTranspose2d(k2,s2) (utils.py:95-100) become pure channel operations on whole tiles
+// (four accumulators in tensor memory), with plain TMA boxes and plain coalesced stores.  Activations that feed GEMMs
+// are "split maps" [2 (hi|lo)][C][ntot] fp16.  The reference's NCHW fp32 tensors exist only at the API boundary.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <memory>
+#include <mutex>
+
+#include "v2_host.cuh"
+#include "urnn_internal.h"
+
+namespace urnn {
+namespace v2 {
+
+// ------------------------------------------------------------------------------------------------ layout
+struct Layout {
+    int H, W, phased;            // phased = 0: plain layout (stand-alone cell): pixel y*W + x, one block
+    long long n4, n4p;           // quarter-resolution pixels, padded to whole tiles
+    long long ntot[3];           // pixels per plane at full / half / quarter resolution (padded)
+    long long blk_stride, blk_valid;
+};
+static Layout make_layout(int H, int W, bool phased) {
+    Layout l; l.H = H; l.W = W; l.phased = phased ? 1 : 0;
+    if (phased) {
+        l.n4 = (long long)(H / 4) * (W / 4); l.n4p = (l.n4 + 127) / 128 * 128;
+        l.ntot[0] = 16 * l.n4p; l.ntot[1] = 4 * l.n4p; l.ntot[2] = l.n4p;
+        l.blk_stride = l.n4p; l.blk_valid = l.n4;
+    } else {
+        l.n4 = (long long)H * W; l.n4p = (l.n4 + 127) / 128 * 128;
+        l.ntot[0] = l.ntot[1] = l.ntot[2] = l.n4p;
+        l.blk_stride = l.n4p; l.blk_valid = l.n4;
+    }
+    return l;
+}
+// position of pixel (y, x) of a level-`level` map (h = H >> level rows) in the internal order
+__host__ __device__ static inline long long ix_internal(int phased, int level, int y, int x, int w_level, int w4, long long n4p) {
+    if (!phased) return (long long)y * w_level + x;
+    if (level == 0) return (long long)((((y & 1) * 2 + (x & 1)) * 4) + (((y >> 1) & 1) * 2 + ((x >> 1) & 1))) * n4p + (long long)(y >> 2) * w4 + (x >> 2);
+    if (level == 1) return (long long)((y & 1) * 2 + (x & 1)) * n4p + (long long)(y >> 1) * w4 + (x >> 1);
+    return (long long)y * w4 + x;
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise kernels
+// NCHW fp32 -> split map (API boundary, once per sequence / per stand-alone call)
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ src, sp16* __restrict__ hi, long long lo_off,
+                                                   int C, int h, int w, int phased, int level, int w4, long long n4p, long long ntot) {
+    const long long total = (long long)C * h * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w); const long long r = i / w; const int y = (int)(r % h); const int c = (int)(r / h);
+        const uint32_t s = split16(__ldg(src + i));
+        const long long o = (long long)c * ntot + ix_internal(phased, level, y, x, w, w4, n4p);
+        reinterpret_cast<unsigned short*>(hi)[o] = (unsigned short)(s & 0xFFFFu);
+        reinterpret_cast<unsigned short*>(hi)[lo_off + o] = (unsigned short)(s >> 16);
+    }
+}
+// split map -> NCHW fp32
+__global__ void __launch_bounds__(256) unpack_kernel(const sp16* __restrict__ hi, long long lo_off, float* __restrict__ dst,
+                                                     int C, int h, int w, int phased, int level, int w4, long long n4p, long long ntot) {
+    const long long total = (long long)C * h * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w); const long long r = i / w; const int y = (int)(r % h); const int c = (int)(r / h);
+        const long long o = (long long)c * ntot + ix_internal(phased, level, y, x, w, w4, n4p);
+        dst[i] = lo16_to_f32(reinterpret_cast<const unsigned short*>(hi)[o]) + lo16_to_f32(reinterpret_cast<const unsigned short*>(hi)[lo_off + o]);
+    }
+}
+
+// h' = (1-z) h + z tanh(GN2(C)),  z = sigmoid(GN1(G_z))  (ConvRNN.py:160-162,180,185,189).  G_z, C: fp32 [F][ntot];
+// h, h': split maps.  One thread = 8 consecutive pixels of one channel (16/32-byte vectors).
+struct BlendArgs {
+    const float* Gz; const float* C; const sp16* h; long long h_lo; sp16* ho; long long ho_lo;
+    const float *sc1, *sh1, *sc2, *sh2; int F; long long ntot;
+};
+__global__ void __launch_bounds__(256) blend_kernel(const BlendArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long nvec = a.ntot >> 3, total = nvec * a.F;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx / nvec);
+    const long long e = (long long)c * a.ntot + (idx - (long long)c * nvec) * 8;
+    const float4 g0 = __ldcs(reinterpret_cast<const float4*>(a.Gz + e)), g1 = __ldcs(reinterpret_cast<const float4*>(a.Gz + e) + 1);
+    const float4 c0 = __ldcs(reinterpret_cast<const float4*>(a.C + e)), c1 = __ldcs(reinterpret_cast<const float4*>(a.C + e) + 1);
+    const uint4 hh = __ldcs(reinterpret_cast<const uint4*>(a.h + e)), hl = __ldcs(reinterpret_cast<const uint4*>(a.h + a.h_lo + e));
+    const float a1 = __ldg(a.sc1 + c), b1 = __ldg(a.sh1 + c), a2 = __ldg(a.sc2 + c), b2 = __ldg(a.sh2 + c);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w}, lw[4] = {hl.x, hl.y, hl.z, hl.w};
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float h0 = lo16_to_f32(hw[u]) + lo16_to_f32(lw[u]), h1 = hi16_to_f32(hw[u]) + hi16_to_f32(lw[u]);
+        const float z0 = sigmoid_fast(fmaf(gv[2 * u], a1, b1)), z1 = sigmoid_fast(fmaf(gv[2 * u + 1], a1, b1));
+        const float t0 = tanh_fast(fmaf(cv[2 * u], a2, b2)), t1 = tanh_fast(fmaf(cv[2 * u + 1], a2, b2));
+        split16x2(fmaf(z0, t0 - h0, h0), fmaf(z1, t1 - h1, h1), oh[u], ol[u]);
+    }
+    *reinterpret_cast<uint4*>(a.ho + e) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(a.ho + a.ho_lo + e) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+}
+
+// Encoder stage 1 (encoder.py:142-157): y = LeakyReLU(W x + b), x = the step's NCHW fp32 input, y -> split map in the
+// internal layout.  fp32 FFMA (C_in = 63 or 3 channels: HBM-bound).  One thread = one image row of a 4x4 patch (4 pixels,
+// one 16-byte load per channel), up to 16 output channels per pass.
+struct Stem1Args {
+    const float* x; int cin; const float* w; long long w_ld; const float* b; int cout; float slope;
+    int H, W, w4, phased; long long n4p, ntot;
+    sp16* out; long long out_lo;
+};
+__global__ void __launch_bounds__(128) stem1_kernel(const Stem1Args a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    extern __shared__ float sw[];                         // [cout][cin] then bias[cout]
+    for (int i = threadIdx.x; i < a.cout * a.cin; i += blockDim.x) sw[i] = __ldg(a.w + (long long)(i / a.cin) * a.w_ld + (i % a.cin));
+    asm volatile("griddepcontrol.wait;" ::: "memory");    // the per-step bias of the event mode is written by an earlier kernel
+    for (int i = threadIdx.x; i < a.cout; i += blockDim.x) sw[a.cout * a.cin + i] = __ldg(a.b + i);
+    __syncthreads();
+    const long long nthr = (long long)a.H * a.w4;         // threads: (y, qx)
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthr) return;
+    const int qx = (int)(t % a.w4), y = (int)(t / a.w4);
+    const long long plane = (long long)a.H * a.W;
+    const float* xp = a.x + (long long)y * a.W + 4 * qx;
+    for (int o0 = 0; o0 < a.cout; o0 += 16) {
+        float acc[16][4];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) { const float bv = (o0 + o < a.cout) ? sw[a.cout * a.cin + o0 + o] : 0.f; acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = bv; }
+        for (int c = 0; c < a.cin; ++c) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(xp + (long long)c * plane));
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                const float wv = (o0 + o < a.cout) ? sw[(o0 + o) * a.cin + c] : 0.f;
+                acc[o][0] = fmaf(wv, v.x, acc[o][0]); acc[o][1] = fmaf(wv, v.y, acc[o][1]);
+                acc[o][2] = fmaf(wv, v.z, acc[o][2]); acc[o][3] = fmaf(wv, v.w, acc[o][3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long pi = ix_internal(a.phased, 0, y, 4 * qx + j, a.W, a.w4, a.n4p);
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                if (o0 + o < a.cout) {
+                    const uint32_t s = split16(lrelu(acc[o][j], a.slope));
+                    const long long e = (long long)(o0 + o) * a.ntot + pi;
+                    reinterpret_cast<unsigned short*>(a.out)[e] = (unsigned short)(s & 0xFFFFu);
+                    reinterpret_cast<unsigned short*>(a.out)[a.out_lo + e] = (unsigned short)(s >> 16);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct Op { int kind; GemmLaunch g; BlendArgs b; };     // kind 0: GEMM, 1: blend
+struct StatBufs { float4* partial; double* total; unsigned* counter; };
+
+struct Plan {
+    urnn_ed_desc d; urnn_ed_params p;
+    Layout lay; int num_sms; int device;
+    SplitMap st[2][6];                         // recurrent states, ping-pong (reference order: e1 e2 e3 d(1/4) d(1/2) d(1x))
+    SplitMap s[3], up3, up2;                   // stem outputs, deconv outputs
+    float *G, *C, *feat;                       // pre-GN maps (largest cell), decoder features (NCHW fp32)
+    void* head_ws; size_t head_ws_bytes;
+    char* wimg; size_t wimg_cap, wimg_used;
+    WImgBatch wb;
+    char* stat_base; size_t stat_bytes;
+    std::vector<Op> ops[2];                    // the step after stage 1, before the head, per state parity
+    size_t total;
+    int lvl_of_state[6]; int ch_of_state[6];
+    bool weights_ready;
+};
+
+static inline int state_level(int k) { const int sc[6] = {0, 1, 2, 2, 1, 0}; return sc[k]; }
+
+struct ArenaW {                                // bump allocator (sizes only when base == nullptr)
+    char* base; size_t off;
+    template <class T> T* take(size_t n) { off = (off + 255) / 256 * 256; T* r = base ? (T*)(base + off) : nullptr; off += n * sizeof(T); return r; }
+};
+
+static SplitMap take_map(ArenaW& a, int C, long long ntot) { SplitMap m; m.C = C; m.ntot = ntot; m.hi = a.take<sp16>((size_t)2 * C * ntot); return m; }
+
+static int layout_plan(Plan& pl, const urnn_ed_desc* d, void* ws) {
+    const Layout& l = pl.lay;
+    ArenaW a{(char*)ws, 0};
+    pl.wimg_cap = (size_t)12 << 20; pl.wimg = a.take<char>(pl.wimg_cap);
+    pl.stat_bytes = (size_t)1 << 20; pl.stat_base = a.take<char>(pl.stat_bytes);
+    const int ch[6] = {d->enc_gru[0], d->enc_gru[1], d->enc_gru[2], d->dec_gru[0], d->dec_gru[1], d->dec_gru[2]};
+    for (int k = 0; k < 6; ++k) { pl.lvl_of_state[k] = state_level(k); pl.ch_of_state[k] = ch[k]; }
+    for (int q = 0; q < 2; ++q) for (int k = 0; k < 6; ++k) pl.st[q][k] = take_map(a, ch[k], l.ntot[state_level(k)]);
+    for (int k = 0; k < 3; ++k) pl.s[k] = take_map(a, d->enc_conv[k], l.ntot[k]);
+    pl.up3 = take_map(a, d->dec_conv[0], l.ntot[1]);
+    pl.up2 = take_map(a, d->dec_conv[1], l.ntot[0]);
+    size_t gmax = 0, cmax = 0;
+    for (int k = 0; k < 6; ++k) { const size_t n = (size_t)l.ntot[state_level(k)]; gmax = std::max(gmax, 2 * (size_t)ch[k] * n); cmax = std::max(cmax, (size_t)ch[k] * n); }
+    pl.G = a.take<float>(gmax); pl.C = a.take<float>(cmax);
+    pl.feat = a.take<float>((size_t)d->dec_conv[2] * d->H * d->W);
+    pl.head_ws_bytes = head_fwd_fp32_workspace(d->H, d->W);
+    pl.head_ws = a.take<char>(pl.head_ws_bytes);
+    pl.total = (a.off + 255) / 256 * 256;
+    return URNN_OK;
+}
+
+struct StatAlloc { char* base; size_t off, cap; };
+static char* sa_take(StatAlloc& sa, size_t bytes) { sa.off = (sa.off + 255) / 256 * 256; char* r = sa.base + sa.off; sa.off += bytes; return r; }
+static bool take_stats(StatAlloc& sa, int nsets, int stride, StatBufs* sb) {
+    sb->partial = (float4*)sa_take(sa, (size_t)nsets * stride * sizeof(float4));
+    sb->total = (double*)sa_take(sa, (size_t)nsets * 4 * sizeof(double));
+    sb->counter = (unsigned*)sa_take(sa, sizeof(unsigned));
+    return sa.off <= sa.cap;
+}
+static bool take_affine(StatAlloc& sa, int nch, float** scale, float** shift) {
+    *scale = (float*)sa_take(sa, (size_t)nch * sizeof(float)); *shift = (float*)sa_take(sa, (size_t)nch * sizeof(float));
+    return sa.off <= sa.cap;
+}
+
+// registers the weight image of a launch; returns its device address
+static const void* add_wimg(Plan& pl, const float* W, long long w_ld, long long w_ks, long long w_acc, int racc, int nrows, int nrows_valid, int K, int k_skip) {
+    if (pl.wb.n >= WIMG_MAX) return nullptr;
+    const size_t bytes = (wimg_bytes(nrows, K) + 255) / 256 * 256;
+    if (pl.wimg_used + bytes > pl.wimg_cap) return nullptr;
+    WImgSpec& S = pl.wb.s[pl.wb.n++];
+    S.W = W; S.w_ld = w_ld; S.w_ks = w_ks; S.w_acc = w_acc; S.racc = racc; S.nrows = nrows; S.nrows_valid = nrows_valid; S.K = K; S.k_skip = k_skip;
+    S.off = pl.wimg_used; pl.wimg_used += bytes;
+    return pl.wimg + S.off;
+}
+
+static void fill_common(GemmParams& P, const Plan& pl, int level) {
+    P.ntot = pl.lay.ntot[level]; P.blk_stride = pl.lay.blk_stride; P.blk_valid = pl.lay.blk_valid; P.nmma = 3; P.slope = pl.d.lrelu_slope;
+}
+
+// One (Skip-)ConvGRU cell step (ConvRNN.py:140-190) as sweep A (gates, GN-1 statistics), sweep B (candidate, GN-2
+// statistics) and the blend.  x / e may be absent (decoder stage 3: x = None -> its weight columns are skipped; encoder: no e).
+static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
+                      const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity) {
+    const int F = cd.F, Cx = cd.Cx;
+    const int Ch = cd.variant == URNN_CELL_DECODER ? 2 * F : F;
+    const int Ktot = Cx + Ch, kskip = x ? 0 : Cx, Keff = Ktot - kskip;
+    const long long ntot = pl.lay.ntot[level];
+    if (F % 32 || (x && x->C % 16) || Keff % 16) { set_error("cell(f16x3): channel counts must be multiples of 16 (Cx=%d F=%d)", Cx, F); return URNN_E_UNSUPPORTED; }
+    CommDev comm; current_comm(&comm);
+    // ---- sweep A: G = W1 u + b1 (2F channels), in chunks of output channels whose hi+lo weight image fits beside the ring
+    const int nkb = (Keff + 63) / 64;
+    int nchunk = 1;
+    while ((size_t)2 * (2 * F / nchunk) * nkb * 128 > (size_t)150 * 1024) nchunk *= 2;      // N=2F: <= ~150 KB of weights
+    if ((2 * F / nchunk) % 32) { set_error("cell(f16x3): cannot split %d gate channels", 2 * F); return URNN_E_UNSUPPORTED; }
+    float *scale1 = nullptr, *shift1 = nullptr;
+    if (!take_affine(sa, 2 * F, &scale1, &shift1)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
+    for (int ci = 0; ci < nchunk; ++ci) {
+        const int N = 2 * F / nchunk, n0 = ci * N;
+        Op op; op.kind = 0; memset(&op.g, 0, sizeof(op.g)); params_defaults(op.g.P);
+        GemmParams& P = op.g.P; fill_common(P, pl, level);
+        int k = 0, m = 0;
+        const SplitMap* segs[3] = {nullptr, nullptr, nullptr};
+        if (x) { segs[m] = x; k = add_segment_steps(op.g, m, x->C, k, 0, 0); ++m; }
+        if (e) { segs[m] = e; k = add_segment_steps(op.g, m, e->C, k, 0, 0); ++m; }
+        segs[m] = &h; k = add_segment_steps(op.g, m, h.C, k, 0, 0); ++m;
+        for (int i = 0; i < 3; ++i) { const SplitMap* sm = segs[i] ? segs[i] : &h; URNN_TRY(make_split_tmap(&op.g.maps[i], *sm, sm->C % 32 == 0 ? 32 : 16, 2)); }
+        P.N = N; P.nrows = N; P.nkb = nkb;
+        P.wimg = first_parity ? add_wimg(pl, cp.w1 + (long long)n0 * Ktot, Ktot, 1, 0, 1 << 30, N, N, Keff, kskip) : nullptr;
+        P.bias = cp.b1 + n0; P.nbias = N;
+        P.epi = EPI_STATS_F32; P.out_f32 = pl.G + (long long)n0 * ntot; P.out_plane = ntot; P.store_c0 = 0; P.store_c1 = N;
+        StatBufs sb;
+        if (!take_stats(sa, N / 32, pl.num_sms, &sb)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
+        P.nstat = N / 32;
+        P.sink.partial = sb.partial; P.sink.total = sb.total; P.sink.counter = sb.counter; P.sink.nsets = N / 32; P.sink.stride = pl.num_sms; P.sink.comm = comm;
+        P.aff.scale = scale1 + n0; P.aff.shift = shift1 + n0; P.aff.gamma = cp.gn1_w + n0; P.aff.beta = cp.gn1_b + n0; P.aff.channels = N; P.aff.ch_per_set = 32; P.aff.eps = cd.eps;
+        URNN_TRY(plan_gemm(op.g, pl.num_sms));
+        ops.push_back(op);
+    }
+    // ---- sweep B: C = W2 [x | e | r*h] + b2,  r = sigmoid(GN1(G)[F:2F]) applied by the gate warps
+    float *scale2 = nullptr, *shift2 = nullptr;
+    {
+        Op op; op.kind = 0; memset(&op.g, 0, sizeof(op.g)); params_defaults(op.g.P);
+        GemmParams& P = op.g.P; fill_common(P, pl, level);
+        int k = 0, m = 0;
+        const SplitMap* segs[3] = {nullptr, nullptr, nullptr};
+        if (x) { segs[m] = x; k = add_segment_steps(op.g, m, x->C, k, 0, 0); ++m; }
+        if (e) { segs[m] = e; k = add_segment_steps(op.g, m, e->C, k, 0, 0); ++m; }
+        for (int i = 0; i < 3; ++i) { const SplitMap* sm = segs[i] ? segs[i] : &h; URNN_TRY(make_split_tmap(&op.g.maps[i], *sm, sm->C % 32 == 0 ? 32 : 16, 2)); }
+        P.gate_ch = F; P.gate_k0 = k; P.gate_h = h.hi; P.gate_h_plane = ntot; P.gate_h_lo = h.lo_off();
+        P.gate_pre = pl.G + (long long)F * ntot; P.gate_pre_plane = ntot; P.gate_scale = scale1 + F; P.gate_shift = shift1 + F;
+        P.N = F; P.nrows = F; P.nkb = nkb;
+        P.wimg = first_parity ? add_wimg(pl, cp.w2, Ktot, 1, 0, 1 << 30, F, F, Keff, kskip) : nullptr;
+        P.bias = cp.b2; P.nbias = F;
+        P.epi = EPI_STATS_F32; P.out_f32 = pl.C; P.out_plane = ntot; P.store_c0 = 0; P.store_c1 = F;
+        StatBufs sb;
+        if (!take_stats(sa, F / 32, pl.num_sms, &sb) || !take_affine(sa, F, &scale2, &shift2)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
+        P.nstat = F / 32;
+        P.sink.partial = sb.partial; P.sink.total = sb.total; P.sink.counter = sb.counter; P.sink.nsets = F / 32; P.sink.stride = pl.num_sms; P.sink.comm = comm;
+        P.aff.scale = scale2; P.aff.shift = shift2; P.aff.gamma = cp.gn2_w; P.aff.beta = cp.gn2_b; P.aff.channels = F; P.aff.ch_per_set = 32; P.aff.eps = cd.eps;
+        URNN_TRY(plan_gemm(op.g, pl.num_sms));
+        ops.push_back(op);
+    }
+    // ---- blend
+    {
+        Op op; op.kind = 1; memset(&op.g, 0, sizeof(op.g));
+        op.b = BlendArgs{pl.G, pl.C, h.hi, h.lo_off(), hout.hi, hout.lo_off(), scale1, shift1, scale2, shift2, F, ntot};
+        ops.push_back(op);
+    }
+    return URNN_OK;
+}
+
+// 1x1 conv + LeakyReLU + AvgPool2 (encoder stages 2, 3): four phase accumulators, averaged in the epilogue
+static int build_pool_stem(Plan& pl, std::vector<Op>& ops, const SplitMap& src, int src_level, const SplitMap& dst, const float* w, const float* b, bool first_parity) {
+    const int Cin = src.C, Cout = dst.C;
+    if (Cin % 16 || Cout % 16 || Cout > 128) { set_error("pooled stem(f16x3): %d -> %d channels not supported", Cin, Cout); return URNN_E_UNSUPPORTED; }
+    Op op; op.kind = 0; memset(&op.g, 0, sizeof(op.g)); params_defaults(op.g.P);
+    GemmParams& P = op.g.P; fill_common(P, pl, src_level + 1);
+    P.nacc = 4; P.acc_mode = ACC_POOL;
+    const long long phase_stride = pl.lay.phased ? pl.lay.ntot[src_level + 1] : 0;
+    for (int a = 0; a < 4; ++a) add_segment_steps(op.g, 0, Cin, 0, a, a * phase_stride);
+    for (int i = 0; i < 3; ++i) URNN_TRY(make_split_tmap(&op.g.maps[i], src, Cin % 32 == 0 ? 32 : 16, 2));
+    P.N = Cout; P.nrows = Cout; P.nkb = (Cin + 63) / 64;
+    P.wimg = first_parity ? add_wimg(pl, w, Cin, 1, 0, 1 << 30, Cout, Cout, Cin, 0) : nullptr;
+    P.bias = b; P.nbias = Cout;
+    P.epi = EPI_LRELU_SPLIT; P.out_hi = dst.hi; P.out_lo = dst.lo_off(); P.out_plane = dst.ntot;
+    URNN_TRY(plan_gemm(op.g, pl.num_sms));
+    ops.push_back(op);
+    return URNN_OK;
+}
+
+// ConvTranspose2d(k2,s2) + LeakyReLU (decoder stages 3, 2): phase a = dy*2 + dx of the fine map is an accumulator;
+// launches cover as many phases as fit (weights hi+lo resident, <= 512 TMEM columns)
+static int build_deconv(Plan& pl, std::vector<Op>& ops, const SplitMap& src, int src_level, const SplitMap& dst, const float* w, const float* b, bool first_parity) {
+    const int Cin = src.C, Cout = dst.C;
+    if (Cin % 16 || Cout % 16 || Cout > 128) { set_error("deconv(f16x3): %d -> %d channels not supported", Cin, Cout); return URNN_E_UNSUPPORTED; }
+    const int nkb = (Cin + 63) / 64;
+    int per = 4;
+    while (per > 1 && (size_t)2 * per * Cout * nkb * 128 > (size_t)110 * 1024) per /= 2;
+    for (int a0 = 0; a0 < 4; a0 += per) {
+        Op op; op.kind = 0; memset(&op.g, 0, sizeof(op.g)); params_defaults(op.g.P);
+        GemmParams& P = op.g.P; fill_common(P, pl, src_level);
+        P.nacc = per; P.acc_mode = ACC_DECONV;
+        add_segment_steps(op.g, 0, Cin, 0, 0, 0);
+        for (int i = 0; i < 3; ++i) URNN_TRY(make_split_tmap(&op.g.maps[i], src, Cin % 32 == 0 ? 32 : 16, 2));
+        P.N = Cout; P.nrows = per * Cout; P.nkb = nkb;
+        // weight (Cin, Cout, 2, 2): row n = a*Cout + co of this launch <-> element [ci][co][a0 + a]
+        P.wimg = first_parity ? add_wimg(pl, w + a0, 4, (long long)Cout * 4, 1, Cout, per * Cout, per * Cout, Cin, 0) : nullptr;
+        P.bias = b; P.nbias = per * Cout; P.bias_mod = Cout;
+        P.epi = EPI_LRELU_SPLIT;
+        const long long blk = pl.lay.phased ? src.ntot : 0;       // fine-map phase a lives `blk` pixels after phase a-1
+        P.out_hi = dst.hi + (long long)a0 * blk; P.out_lo = dst.lo_off(); P.out_plane = dst.ntot; P.out_acc_stride = blk;
+        URNN_TRY(plan_gemm(op.g, pl.num_sms));
+        ops.push_back(op);
+    }
+    return URNN_OK;
+}
+
+// decoder stage 1 stem: 1x1 conv + LeakyReLU -> decoder features as NCHW fp32 (the head's input, flood_head.py:131)
+static int build_final_stem(Plan& pl, std::vector<Op>& ops, const SplitMap& src, const float* w, const float* b, int Cout, bool first_parity) {
+    const int Cin = src.C;
+    if (Cin % 16 || Cout % 16 || Cout > 256) { set_error("final stem(f16x3): %d -> %d channels not supported", Cin, Cout); return URNN_E_UNSUPPORTED; }
+    Op op; op.kind = 0; memset(&op.g, 0, sizeof(op.g)); params_defaults(op.g.P);
+    GemmParams& P = op.g.P; fill_common(P, pl, 0);
+    add_segment_steps(op.g, 0, Cin, 0, 0, 0);
+    for (int i = 0; i < 3; ++i) URNN_TRY(make_split_tmap(&op.g.maps[i], src, Cin % 32 == 0 ? 32 : 16, 2));
+    P.N = Cout; P.nrows = Cout; P.nkb = (Cin + 63) / 64;
+    P.wimg = first_parity ? add_wimg(pl, w, Cin, 1, 0, 1 << 30, Cout, Cout, Cin, 0) : nullptr;
+    P.bias = b; P.nbias = Cout;
+    P.epi = EPI_LRELU_F32; P.out_f32 = pl.feat; P.out_plane = (long long)pl.d.H * pl.d.W; P.store_c0 = 0; P.store_c1 = Cout;
+    P.nchw = pl.lay.phased; P.nchw_w = pl.d.W; P.nchw_w4 = pl.d.W / 4; P.nchw_n4p = pl.lay.n4p;
+    URNN_TRY(plan_gemm(op.g, pl.num_sms));
+    ops.push_back(op);
+    return URNN_OK;
+}
+
+size_t step_workspace_bytes(const urnn_ed_desc* d) {
+    Plan pl; pl.d = *d; pl.lay = make_layout(d->H, d->W, true);
+    layout_plan(pl, d, nullptr);
+    return pl.total;
+}
+
+static int check_desc(const urnn_ed_desc* d) {
+    URNN_CHECK_ARG(d && d->H > 0 && d->W > 0 && d->H % 4 == 0 && d->W % 4 == 0, "ed(f16x3): H, W must be positive multiples of 4");
+    URNN_CHECK_ARG(d->ksize == 1, "ed(f16x3): filter_size must be 1");
+    URNN_CHECK_ARG(d->dec_conv[2] == 16, "ed: decoder.conv_out_channels[-1]=%d must be 16 (head width, model.py:62-63)", d->dec_conv[2]);
+    URNN_CHECK_ARG(d->dec_gru[0] == d->enc_gru[2] && d->dec_gru[1] == d->enc_gru[1] && d->dec_gru[2] == d->enc_gru[0],
+                   "ed: decoder gru_channels must mirror the encoder's (skip concat, decoder.py:135)");
+    URNN_CHECK_ARG((long long)d->H * d->W < (1LL << 30), "ed(f16x3): more than 2^30 cells per map are not supported");
+    return URNN_OK;
+}
+
+// Builds the plan: workspace carving, tensor maps, launch planning for both state parities (host work only).
+int build_plan(Plan& pl, const urnn_ed_desc* d, const urnn_ed_params* p, void* ws, size_t ws_bytes) {
+    URNN_TRY(check_desc(d));
+    pl.d = *d; pl.p = *p; pl.lay = make_layout(d->H, d->W, true);
+    URNN_CUDA(cudaGetDevice(&pl.device));
+    URNN_CUDA(cudaDeviceGetAttribute(&pl.num_sms, cudaDevAttrMultiProcessorCount, pl.device));
+    layout_plan(pl, d, ws);
+    if (pl.total > ws_bytes) { set_error("ed(f16x3): workspace %zu < %zu bytes", ws_bytes, pl.total); return URNN_E_WORKSPACE; }
+    pl.wb.n = 0; pl.wb.base = pl.wimg; pl.wimg_used = 0; pl.weights_ready = false;
+    StatAlloc sa{pl.stat_base, 0, pl.stat_bytes};
+    urnn_cell_desc enc[3], dec[3];
+    for (int k = 0; k < 3; ++k) {
+        enc[k] = urnn_cell_desc{d->H >> k, d->W >> k, d->enc_conv[k], d->enc_gru[k], 1, URNN_CELL_ENCODER, d->math, d->gn_eps};
+        const int sc = 2 - k;
+        dec[k] = urnn_cell_desc{d->H >> sc, d->W >> sc, (k == 0) ? d->dec_conv[0] : d->dec_conv[k - 1], d->dec_gru[k], 1, URNN_CELL_DECODER, d->math, d->gn_eps};
+    }
+    for (int q = 0; q < 2; ++q) {
+        std::vector<Op>& ops = pl.ops[q];
+        ops.clear();
+        const bool fp = q == 0;
+        StatAlloc sq = sa;                         // both parities share the statistics buffers (they never overlap in time)
+        SplitMap* in = pl.st[q]; SplitMap* out = pl.st[q ^ 1];
+        // encoder (encoder.py:187-215)
+        URNN_TRY(build_cell(pl, ops, sq, enc[0], p->enc_cell[0], 0, &pl.s[0], nullptr, in[0], out[0], fp));
+        URNN_TRY(build_pool_stem(pl, ops, out[0], 0, pl.s[1], p->enc_stem_w[1], p->enc_stem_b[1], fp));
+        URNN_TRY(build_cell(pl, ops, sq, enc[1], p->enc_cell[1], 1, &pl.s[1], nullptr, in[1], out[1], fp));
+        URNN_TRY(build_pool_stem(pl, ops, out[1], 1, pl.s[2], p->enc_stem_w[2], p->enc_stem_b[2], fp));
+        URNN_TRY(build_cell(pl, ops, sq, enc[2], p->enc_cell[2], 2, &pl.s[2], nullptr, in[2], out[2], fp));
+        // decoder (decoder.py:173-217): deepest first; stage 3 has no x (ConvRNN.py:143-146)
+        URNN_TRY(build_cell(pl, ops, sq, dec[0], p->dec_cell[0], 2, nullptr, &out[2], in[3], out[3], fp));
+        URNN_TRY(build_deconv(pl, ops, out[3], 2, pl.up3, p->dec_stem_w[0], p->dec_stem_b[0], fp));
+        URNN_TRY(build_cell(pl, ops, sq, dec[1], p->dec_cell[1], 1, &pl.up3, &out[1], in[4], out[4], fp));
+        URNN_TRY(build_deconv(pl, ops, out[4], 1, pl.up2, p->dec_stem_w[1], p->dec_stem_b[1], fp));
+        URNN_TRY(build_cell(pl, ops, sq, dec[2], p->dec_cell[2], 0, &pl.up2, &out[0], in[5], out[5], fp));
+        URNN_TRY(build_final_stem(pl, ops, out[5], p->dec_stem_w[2], p->dec_stem_b[2], d->dec_conv[2], fp));
+        if (q == 1) {                              // weight images are shared: copy the addresses recorded for parity 0
+            size_t gi = 0;
+            for (size_t i = 0; i < ops.size(); ++i) if (ops[i].kind == 0) { while (pl.ops[0][gi].kind != 0) ++gi; ops[i].g.P.wimg = pl.ops[0][gi].g.P.wimg; ++gi; }
+        }
+    }
+    for (const Op& op : pl.ops[0]) if (op.kind == 0 && op.g.P.wimg == nullptr) { set_error("ed(f16x3): weight image arena too small"); return URNN_E_WORKSPACE; }
+    return URNN_OK;
+}
+
+// device work that has to precede the first step: counters, weight images
+int prepare(Plan& pl, cudaStream_t st) {
+    URNN_CUDA(cudaMemsetAsync(pl.stat_base, 0, pl.stat_bytes, st));
+    wimg_kernel<<<dim3(16, pl.wb.n), 256, 0, st>>>(pl.wb);
+    URNN_LAUNCH_CHECK();
+    pl.weights_ready = true;
+    return URNN_OK;
+}
+
+static int launch_pack(const float* src, const SplitMap& m, int C, int h, int w, const Layout& l, int level, cudaStream_t st) {
+    const long long total = (long long)C * h * w;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    pack_kernel<<<grid, 256, 0, st>>>(src, m.hi, m.lo_off(), C, h, w, l.phased, level, l.W / 4, l.n4p, m.ntot);
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
+static int launch_unpack(const SplitMap& m, float* dst, int C, int h, int w, const Layout& l, int level, cudaStream_t st) {
+    const long long total = (long long)C * h * w;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    unpack_kernel<<<grid, 256, 0, st>>>(m.hi, m.lo_off(), dst, C, h, w, l.phased, level, l.W / 4, l.n4p, m.ntot);
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
+
+int load_states(Plan& pl, int parity, const float* const* s_nchw, cudaStream_t st) {
+    for (int k = 0; k < 6; ++k) {
+        const int lv = pl.lvl_of_state[k];
+        URNN_TRY(launch_pack(s_nchw[k], pl.st[parity][k], pl.ch_of_state[k], pl.d.H >> lv, pl.d.W >> lv, pl.lay, lv, st));
+    }
+    return URNN_OK;
+}
+int store_states(Plan& pl, int parity, float* const* s_nchw, cudaStream_t st) {
+    for (int k = 0; k < 6; ++k) {
+        const int lv = pl.lvl_of_state[k];
+        URNN_TRY(launch_unpack(pl.st[parity][k], s_nchw[k], pl.ch_of_state[k], pl.d.H >> lv, pl.d.W >> lv, pl.lay, lv, st));
+    }
+    return URNN_OK;
+}
+
+static int launch_ew(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    URNN_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
+
+// One time step: states of `parity` -> states of `parity ^ 1`, depth/probability maps -> out (2, H, W).
+int step(Plan& pl, int parity, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st) {
+    const urnn_ed_desc& d = pl.d;
+    {
+        Stem1Args a{x, cin, w, w_ld, b, d.enc_conv[0], d.lrelu_slope, d.H, d.W, d.W / 4, pl.lay.phased, pl.lay.n4p, pl.s[0].ntot, pl.s[0].hi, pl.s[0].lo_off()};
+        const long long nthr = (long long)d.H * (d.W / 4);
+        const size_t smem = ((size_t)d.enc_conv[0] * cin + d.enc_conv[0]) * sizeof(float);
+        if (smem > 48 * 1024) { set_error("stage-1 stem: %d x %d weights exceed 48 KB of shared memory", d.enc_conv[0], cin); return URNN_E_UNSUPPORTED; }
+        void* args[1] = {(void*)&a};
+        URNN_TRY(launch_ew((const void*)stem1_kernel, dim3((unsigned)((nthr + 127) / 128)), dim3(128), smem, st, args));
+    }
+    for (const Op& op : pl.ops[parity]) {
+        if (op.kind == 0) URNN_TRY(launch_gemm(op.g, st));
+        else {
+            const long long total = (op.b.ntot >> 3) * op.b.F;
+            void* args[1] = {(void*)&op.b};
+            URNN_TRY(launch_ew((const void*)blend_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, args));
+        }
+    }
+    return head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, st);
+}
+
+// ------------------------------------------------------------------------------------------------ plan cache (per-step API)
+// urnn_ed_step_fwd is called once per time step by the drop-in ED.forward; building a plan (20 tensor maps, launch
+// planning) costs ~0.1 ms of host time, so the last few plans are kept, keyed by everything they depend on.
+struct CacheKey { int device; urnn_ed_desc d; urnn_ed_params p; void* ws; size_t ws_bytes; };
+static bool same_key(const CacheKey& a, const CacheKey& b) { return memcmp(&a, &b, sizeof(CacheKey)) == 0; }
+struct CacheEnt { CacheKey key; std::unique_ptr<Plan> plan; unsigned long long stamp; };
+static std::mutex g_cache_mu;
+static std::vector<CacheEnt> g_cache;
+static unsigned long long g_stamp = 0;
+
+static int cached_plan(const urnn_ed_desc* d, const urnn_ed_params* p, void* ws, size_t ws_bytes, Plan** out) {
+    CacheKey key; memset(&key, 0, sizeof(key));
+    URNN_CUDA(cudaGetDevice(&key.device));
+    key.d = *d; key.p = *p; key.ws = ws; key.ws_bytes = ws_bytes;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (CacheEnt& e : g_cache) if (same_key(e.key, key)) { e.stamp = ++g_stamp; *out = e.plan.get(); return URNN_OK; }
+    std::unique_ptr<Plan> pl(new Plan());
+    URNN_TRY(build_plan(*pl, d, p, ws, ws_bytes));
+    if (g_cache.size() >= 8) {
+        size_t old = 0;
+        for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].stamp < g_cache[old].stamp) old = i;
+        g_cache.erase(g_cache.begin() + old);
+    }
+    g_cache.push_back(CacheEnt{key, std::move(pl), ++g_stamp});
+    *out = g_cache.back().plan.get();
+    return URNN_OK;
+}
+
+// the reference's one-step contract with fp32 NCHW states in and out (model.py:65-121): convert, step, convert back
+int step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float* x, int cin, const float* w, long long w_ld, const float* b,
+                  const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Plan* pl = nullptr;
+    URNN_TRY(cached_plan(d, p, ws, ws_bytes, &pl));
+    URNN_TRY(prepare(*pl, st));                    // weights may have changed between calls (training): rebuild the images
+    URNN_TRY(load_states(*pl, 0, sin, st));
+    URNN_TRY(step(*pl, 0, x, cin, w, w_ld, b, out, st));
+    return store_states(*pl, 1, sout, st);
+}
+
+}  // namespace v2
+
+// ---- entry points used by capi.cu
+size_t v2_step_workspace_bytes(const urnn_ed_desc* d) { return v2::step_workspace_bytes(d); }
+int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float* x, int cin, const float* w, long long w_ld, const float* b,
+                     const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    return v2::step_fwd_nchw(d, p, x, cin, w, w_ld, b, sin, sout, out, ws, ws_bytes, st);
+}
+V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc) {
+    std::unique_ptr<v2::Plan> pl(new v2::Plan());
+    *rc = v2::build_plan(*pl, d, p, ws, ws_bytes);
+    if (*rc == URNN_OK) *rc = v2::prepare(*pl, st);
+    if (*rc == URNN_OK) *rc = v2::load_states(*pl, 0, states, st);
+    if (*rc != URNN_OK) return nullptr;
+    return reinterpret_cast<V2Seq*>(pl.release());
+}
+int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st) {
+    return v2::step(*reinterpret_cast<v2::Plan*>(s), t & 1, x, cin, w, w_ld, b, out, st);
+}
+int v2_seq_end(V2Seq* s, int T, float* const* states, cudaStream_t st) {
+    std::unique_ptr<v2::Plan> pl(reinterpret_cast<v2::Plan*>(s));
+    return states ? v2::store_states(*pl, T & 1, states, st) : URNN_OK;
+}
+
+}  // namespace urnn

@@ -9,12 +9,12 @@
 namespace urnn {
 namespace v2 {
 
-// A "split map": C channels x ntot pixels stored as bf16 hi planes followed by bf16 lo planes, [2][C][ntot].
+// A "split map": C channels x ntot pixels stored as 16-bit hi planes followed by 16-bit lo planes, [2][C][ntot] (fp16 pairs, see ptx_sm100.cuh).
 // v = hi + lo.  ntot is a multiple of 128; pixels are grouped in blocks of blk_stride of which the first blk_valid are
 // real (phase-separated layout of the encoder-decoder, see layout_v2 in urnn_v2.cu; a plain map is one block).
 struct SplitMap {
-    __nv_bfloat16* hi; int C; long long ntot;
-    __nv_bfloat16* lo() const { return hi + (long long)C * ntot; }
+    sp16* hi; int C; long long ntot;
+    sp16* lo() const { return hi + (long long)C * ntot; }
     long long lo_off() const { return (long long)C * ntot; }
     static size_t bytes(int C, long long ntot) { return (size_t)4 * C * ntot; }
 };
@@ -48,7 +48,7 @@ static inline int make_split_tmap(CUtensorMap* tm, const SplitMap& m, int unit_c
     cuuint64_t strides[2] = {(cuuint64_t)m.ntot * 2, (cuuint64_t)m.C * m.ntot * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)unit_ch, (cuuint32_t)nhl};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, m.hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(tm, (SPLIT_FMT == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 3, m.hi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, l2promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for map C=%d ntot=%lld unit=%d", (int)r, m.C, m.ntot, unit_ch); return URNN_E_CUDA; }
     return URNN_OK;

@@ -67,18 +67,30 @@ class ED(nn.Module):
     def _fused_step(self, x, states):
         dev = x.device
         Cin, H, W = x.shape
-        key = (H, W, Cin, dev, ops.get_default_math())
+        math = self._cells()[0][0].math or ops.get_default_math()
+        key = (H, W, Cin, dev, math)
         if self._plan is None or self._plan[0] != key:
+            # everything that depends only on the geometry is built once: descriptor, workspace, expected shapes
             desc = self.ed_desc(H, W, Cin)
-            self._plan = (key, desc, ops.ed_workspace_bytes(desc))
-        _, desc, nbytes = self._plan
+            stem1 = self._stems()[0][0]._conv()
+            if Cin != stem1.in_channels:
+                raise ValueError(f"input_t has {Cin} channels, encoder.stage1 expects {stem1.in_channels}")
+            ln = self.head.param_dict()["ln_w"][0]
+            if tuple(ln.shape) != (16, H, W):
+                raise ValueError(f"this model's head LayerNorm is built for {tuple(ln.shape[1:])} grids, input_t is {H}x{W} "
+                                 "(checkpoints are resolution-specific, network_blocks.py:93-94)")
+            from urnn_b200.runner import state_shapes
+            enc_cells, dec_cells = self._cells()
+            shapes = state_shapes(H, W, [c.num_features for c in enc_cells], [c.num_features for c in dec_cells])
+            ws = torch.empty(ops.ed_workspace_bytes(desc), dtype=torch.uint8, device=dev)
+            self._plan = (key, desc, ws, shapes)
+        _, desc, ws, shapes = self._plan
         for p in self.parameters():
             if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                 raise RuntimeError("urnn_b200: ED parameters must be contiguous float32 CUDA tensors")
-        sin = [ops._chk(s[0], f"state {i}") for i, s in enumerate(states)]
+        sin = [ops._chk(s[0], f"state {i}", shapes[i]) for i, s in enumerate(states)]
         sout = [torch.empty_like(s) for s in sin]
         out = torch.empty((2, H, W), dtype=torch.float32, device=dev)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         ops.ed_step_fwd(desc, self.ed_params(), ops._chk(x, "input_t"), sin, sout, out, ws)
         return out, sout
 

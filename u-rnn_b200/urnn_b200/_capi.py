@@ -10,8 +10,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("URNN_B200_LIB", os.path.join(HERE, "liburnn_b200.so"))   # override: bring-up only
 
 URNN_CELL_ENCODER, URNN_CELL_DECODER = 0, 1
-MATH_FP32, MATH_BF16 = 0, 2
-MATH_BY_NAME = {"fp32": MATH_FP32, "bf16": MATH_BF16}
+MATH_FP32, MATH_BF16, MATH_F16X3 = 0, 2, 3
+# fp32: FFMA parity mode | f16x3: tcgen05, fp16 hi+lo split operands (the fast mode that meets the T=180 tolerance) |
+# bf16: tcgen05 single-pass bf16 operands (round-1 kernels; short horizons only)
+MATH_BY_NAME = {"fp32": MATH_FP32, "bf16": MATH_BF16, "f16x3": MATH_F16X3}
 
 fp = C.c_void_p   # device pointers travel as integers
 
@@ -83,6 +85,9 @@ SIGNATURES = {
     "urnn_ed_step_workspace_bytes": (sz, [C.POINTER(EdDesc)]),
     "urnn_ed_step_fwd": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), fp, C.POINTER(fp), C.POINTER(fp), fp,
                                    vp, sz, vp]),
+    "urnn_ed_sequence_dev_workspace_bytes": (sz, [C.POINTER(EdDesc)]),
+    "urnn_ed_sequence_dev": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), i32, vp, vp, vp, C.POINTER(fp),
+                                       vp, sz, vp]),
     "urnn_ed_sequence_host_workspace_bytes": (sz, [C.POINTER(EdDesc)]),
     "urnn_ed_sequence_host": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), i32, vp, vp, C.POINTER(fp),
                                         vp, sz, vp]),

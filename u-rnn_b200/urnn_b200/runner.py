@@ -87,6 +87,34 @@ class SequenceRunner:
         return depth, prob, final
 
     @torch.no_grad()
+    def run_dev(self, inputs, states=None, want_prob=True):
+        """The whole loop in ONE library call (urnn_ed_sequence_dev): inputs (T,Cin,H,W) float32 on the device ->
+        (depth (T,H,W), prob (T,H,W) or None, [6 final states]); stream-ordered, no host synchronisation."""
+        lib = _capi.load()
+        T = inputs.shape[0]
+        inputs = ops._chk(inputs, "inputs", (T, self.Cin, self.H, self.W))
+        st = self.states[0]
+        for i, dst in enumerate(st):
+            if states is None:
+                dst.zero_()
+            else:
+                dst.copy_(states[i].reshape(dst.shape))
+        need = lib.urnn_ed_sequence_dev_workspace_bytes(C.byref(self.desc))
+        if need == 0:
+            raise RuntimeError("urnn_ed_sequence_dev_workspace_bytes: " + lib.urnn_last_error().decode())
+        if getattr(self, "_dev_ws", None) is None or self._dev_ws.numel() < need:
+            self._dev_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        depth = torch.empty((T, self.H, self.W), device=self.device)
+        prob = torch.empty((T, self.H, self.W), device=self.device) if want_prob else None
+        params = self.net.ed_params()
+        sp = (C.c_void_p * 6)(*[s.data_ptr() for s in st])
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _capi.check(lib.urnn_ed_sequence_dev(C.byref(self.desc), C.byref(params), T, C.c_void_p(inputs.data_ptr()),
+                                             C.c_void_p(depth.data_ptr()), C.c_void_p(prob.data_ptr()) if want_prob else None, sp,
+                                             C.c_void_p(self._dev_ws.data_ptr()), self._dev_ws.numel(), stream), "urnn_ed_sequence_dev")
+        return depth, prob, [s.clone() for s in st]
+
+    @torch.no_grad()
     def run_host(self, inputs_host, out_host=None, states=None):
         """inputs_host (T,Cin,H,W) float32 HOST tensor (pin it for overlap) -> out_host (T,H,W) host tensor with the
         masked depth maps; one call into the C ABI (urnn_ed_sequence_host), which blocks until the last copy landed."""
