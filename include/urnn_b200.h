@@ -199,6 +199,13 @@ int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t
                          const float* inputs_dev, float* out_dev, float* prob_dev, float* const* states,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* Measurement entry point (URNN_MATH_F16X3): T steps like urnn_ed_sequence_dev (same workspace), every launch bracketed by
+ * CUDA events on `stream`; synchronises once per step.  op_ms[i] = mean milliseconds of launch i, names = max_ops records of
+ * 24 bytes ("stem1", "enc1.A", "enc1.B", "enc1.blend", ..., "head"), *nops = number of launches per step. */
+int urnn_ed_profile_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T, const float* inputs_dev,
+                        float* const* states, void* ws, size_t ws_bytes, void* stream,
+                        float* op_ms, char* names, int32_t max_ops, int32_t* nops);
+
 size_t urnn_ed_sequence_host_workspace_bytes(const urnn_ed_desc* d);
 int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T,
                           const float* inputs_host, float* out_host, float* const* states,

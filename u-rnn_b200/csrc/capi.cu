@@ -463,6 +463,29 @@ int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t
     return URNN_OK;
 }
 
+int urnn_ed_profile_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T, const float* inputs_dev, float* const* states,
+                        void* ws, size_t ws_bytes, void* stream, float* op_ms, char* names, int32_t max_ops, int32_t* nops) {
+    URNN_CHECK_ARG(d && p && inputs_dev && states && T > 0 && op_ms && names && nops, "ed_profile_dev: bad argument");
+#ifndef URNN_NO_TC
+    URNN_CHECK_ARG(d->math == URNN_MATH_F16X3, "ed_profile_dev: only URNN_MATH_F16X3 is instrumented");
+    SeqPlan sp;
+    URNN_TRY(seq_plan(d, ws, ws_bytes, &sp));
+    if (sp.total > ws_bytes) { set_error("ed_profile_dev: workspace %zu < %zu bytes", ws_bytes, sp.total); return URNN_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    SeqGuard sg; int rc = URNN_OK;
+    sg.seq = v2_seq_begin(d, p, states, sp.step_ws, sp.step_ws_bytes, st, &rc);
+    if (!sg.seq) return rc;
+    int n = 0;
+    URNN_TRY(v2_seq_profile(sg.seq, T, inputs_dev, (size_t)d->Cin * d->H * d->W, d->Cin, p->enc_stem_w[0], (long long)d->Cin, p->enc_stem_b[0],
+                            sp.out[0], st, op_ms, names, max_ops, &n));
+    *nops = n;
+    V2Seq* q = sg.seq; sg.seq = nullptr;
+    return v2_seq_end(q, T, states, st);
+#else
+    set_error("ed_profile_dev: built without the tcgen05 path"); return URNN_E_UNSUPPORTED;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ event mode
 __global__ void event_static_maps_kernel(const float* __restrict__ dem, const float* __restrict__ imp,
                                          const float* __restrict__ man, float dem_min, float dem_max,

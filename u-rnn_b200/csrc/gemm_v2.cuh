@@ -179,7 +179,8 @@ struct GemmParams {
     int nchw, nchw_w, nchw_w4; long long nchw_n4p;  // EPI_LRELU_F32: destination is an NCHW image (un-permute the phase-separated layout)
     long long out_acc_stride;                      // ACC_DECONV: pixel offset between the destination blocks of the accumulators
     int nstat; StatSink2 sink; AffineOut aff;      // leading 32-column groups with GroupNorm statistics
-    int l2_ahead;                                  // tiles of L2 prefetch distance (0: off)
+    int l2_ahead;                                  // (unused)
+    unsigned long long l2_hint;                    // L2 eviction policy of the TMA operand loads
     long long* dbg;                                // bring-up: clock64 stamps of CTA 0, [event 0..7][tile 0..31]
     int nslots, tmem_cols, acc_stages, acc_stride; // ring depth; TMEM allocation; stages and column stride between accumulators
 };
@@ -297,8 +298,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
                 const uint32_t dst = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
                 const uint32_t bar = full0 + 8 * slot;
                 mbar_arrive_expect_tx(bar, 2u * pe.half_bytes);
-                tma_load_3d(dst, reinterpret_cast<const void*>(pe.map), bar, px, pe.c0, 0, L2_EVICT_NORMAL);
-                tma_load_3d(dst + pe.half_bytes, reinterpret_cast<const void*>(pe.map), bar, px + 64, pe.c0, 0, L2_EVICT_NORMAL);
+                tma_load_3d(dst, reinterpret_cast<const void*>(pe.map), bar, px, pe.c0, 0, P.l2_hint);
+                tma_load_3d(dst + pe.half_bytes, reinterpret_cast<const void*>(pe.map), bar, px + 64, pe.c0, 0, P.l2_hint);
                 if (s <= 1) V2_STAMP(0 + me, ti);
                 slot += 2; if (slot >= P.nslots) { slot -= P.nslots; ph ^= 1; }
                 s += 2; while (s >= P.nsteps) { s -= P.nsteps; tile += gridDim.x; ++ti; }

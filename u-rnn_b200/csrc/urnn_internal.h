@@ -53,6 +53,8 @@ int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float
                      const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc);
 int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st);
+int v2_seq_profile(V2Seq* s, int T, const float* inputs, size_t in_elems, int cin, const float* w, long long w_ld, const float* b, float* out,
+                   cudaStream_t st, float* op_ms, char* names, int max_ops, int* nops);
 int v2_seq_end(V2Seq* s, int T, float* const* states, cudaStream_t st);
 
 // fp32 FFMA path (urnn_fp32.cu)

@@ -115,12 +115,16 @@ struct Stem1Args {
     int H, W, w4, phased; long long n4p, ntot;
     sp16* out; long long out_lo;
 };
-__global__ void __launch_bounds__(128) stem1_kernel(const Stem1Args a) {
+__global__ void __launch_bounds__(64) stem1_kernel(const Stem1Args a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    extern __shared__ float sw[];                         // [cout][cin] then bias[cout]
-    for (int i = threadIdx.x; i < a.cout * a.cin; i += blockDim.x) sw[i] = __ldg(a.w + (long long)(i / a.cin) * a.w_ld + (i % a.cin));
+    extern __shared__ __align__(16) float sw[];           // weights transposed [cin][16 * npass] (one 64-byte row per channel and pass), then bias
+    const int npass = (a.cout + 15) / 16, ldw = 16 * npass;
+    for (int i = threadIdx.x; i < a.cin * ldw; i += blockDim.x) {
+        const int c = i / ldw, o = i % ldw;
+        sw[i] = o < a.cout ? __ldg(a.w + (long long)o * a.w_ld + c) : 0.f;
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");    // the per-step bias of the event mode is written by an earlier kernel
-    for (int i = threadIdx.x; i < a.cout; i += blockDim.x) sw[a.cout * a.cin + i] = __ldg(a.b + i);
+    for (int i = threadIdx.x; i < ldw; i += blockDim.x) sw[a.cin * ldw + i] = i < a.cout ? __ldg(a.b + i) : 0.f;
     __syncthreads();
     const long long nthr = (long long)a.H * a.w4;         // threads: (y, qx)
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -128,17 +132,47 @@ __global__ void __launch_bounds__(128) stem1_kernel(const Stem1Args a) {
     const int qx = (int)(t % a.w4), y = (int)(t / a.w4);
     const long long plane = (long long)a.H * a.W;
     const float* xp = a.x + (long long)y * a.W + 4 * qx;
-    for (int o0 = 0; o0 < a.cout; o0 += 16) {
+    unsigned short* outp = reinterpret_cast<unsigned short*>(a.out);
+    for (int ps = 0; ps < npass; ++ps) {
         float acc[16][4];
+        const float* bias = sw + a.cin * ldw + 16 * ps;
 #pragma unroll
-        for (int o = 0; o < 16; ++o) { const float bv = (o0 + o < a.cout) ? sw[a.cout * a.cin + o0 + o] : 0.f; acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = bv; }
-        for (int c = 0; c < a.cin; ++c) {
+        for (int o = 0; o < 16; ++o) acc[o][0] = acc[o][1] = acc[o][2] = acc[o][3] = bias[o];
+        const float* wrow = sw + 16 * ps;
+        int c = 0;
+        for (; c + 8 <= a.cin; c += 8) {                  // eight independent 16-byte loads in flight per thread
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(xp + (long long)(c + u) * plane));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4* w4p = reinterpret_cast<const float4*>(wrow + (c + u) * ldw);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = w4p[q];
+                    const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int o = 4 * q + r;
+                        acc[o][0] = fmaf(ww[r], v[u].x, acc[o][0]); acc[o][1] = fmaf(ww[r], v[u].y, acc[o][1]);
+                        acc[o][2] = fmaf(ww[r], v[u].z, acc[o][2]); acc[o][3] = fmaf(ww[r], v[u].w, acc[o][3]);
+                    }
+                }
+            }
+        }
+        for (; c < a.cin; ++c) {
             const float4 v = __ldcs(reinterpret_cast<const float4*>(xp + (long long)c * plane));
+            const float4* w4p = reinterpret_cast<const float4*>(wrow + c * ldw);
 #pragma unroll
-            for (int o = 0; o < 16; ++o) {
-                const float wv = (o0 + o < a.cout) ? sw[(o0 + o) * a.cin + c] : 0.f;
-                acc[o][0] = fmaf(wv, v.x, acc[o][0]); acc[o][1] = fmaf(wv, v.y, acc[o][1]);
-                acc[o][2] = fmaf(wv, v.z, acc[o][2]); acc[o][3] = fmaf(wv, v.w, acc[o][3]);
+            for (int q = 0; q < 4; ++q) {
+                const float4 wv = w4p[q];
+                const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int o = 4 * q + r;
+                    acc[o][0] = fmaf(ww[r], v.x, acc[o][0]); acc[o][1] = fmaf(ww[r], v.y, acc[o][1]);
+                    acc[o][2] = fmaf(ww[r], v.z, acc[o][2]); acc[o][3] = fmaf(ww[r], v.w, acc[o][3]);
+                }
             }
         }
 #pragma unroll
@@ -146,11 +180,11 @@ __global__ void __launch_bounds__(128) stem1_kernel(const Stem1Args a) {
             const long long pi = ix_internal(a.phased, 0, y, 4 * qx + j, a.W, a.w4, a.n4p);
 #pragma unroll
             for (int o = 0; o < 16; ++o) {
-                if (o0 + o < a.cout) {
-                    const uint32_t s = split16(lrelu(acc[o][j], a.slope));
-                    const long long e = (long long)(o0 + o) * a.ntot + pi;
-                    reinterpret_cast<unsigned short*>(a.out)[e] = (unsigned short)(s & 0xFFFFu);
-                    reinterpret_cast<unsigned short*>(a.out)[a.out_lo + e] = (unsigned short)(s >> 16);
+                if (16 * ps + o < a.cout) {
+                    const uint32_t sv = split16(lrelu(acc[o][j], a.slope));
+                    const long long e = (long long)(16 * ps + o) * a.ntot + pi;
+                    outp[e] = (unsigned short)(sv & 0xFFFFu);
+                    outp[a.out_lo + e] = (unsigned short)(sv >> 16);
                 }
             }
         }
@@ -158,7 +192,7 @@ __global__ void __launch_bounds__(128) stem1_kernel(const Stem1Args a) {
 }
 
 // ------------------------------------------------------------------------------------------------ plan
-struct Op { int kind; GemmLaunch g; BlendArgs b; };     // kind 0: GEMM, 1: blend
+struct Op { int kind; GemmLaunch g; BlendArgs b; char name[24]; };     // kind 0: GEMM, 1: blend
 struct StatBufs { float4* partial; double* total; unsigned* counter; };
 
 struct Plan {
@@ -409,19 +443,30 @@ int build_plan(Plan& pl, const urnn_ed_desc* d, const urnn_ed_params* p, void* w
         const bool fp = q == 0;
         StatAlloc sq = sa;                         // both parities share the statistics buffers (they never overlap in time)
         SplitMap* in = pl.st[q]; SplitMap* out = pl.st[q ^ 1];
+        size_t tagged = 0;
+        auto tag = [&](const char* what) {          // names the launches appended since the last call (profiles, urnn_ed_profile_dev)
+            int gi = 0;
+            for (; tagged < ops.size(); ++tagged) {
+                Op& o = ops[tagged];
+                if (o.kind == 1) snprintf(o.name, sizeof(o.name), "%s.blend", what);
+                else if (o.g.P.gate_ch) snprintf(o.name, sizeof(o.name), "%s.B", what);
+                else if (o.g.P.epi == EPI_STATS_F32) snprintf(o.name, sizeof(o.name), gi++ ? "%s.A%d" : "%s.A", what, gi);
+                else snprintf(o.name, sizeof(o.name), gi++ ? "%s.%d" : "%s", what, gi);
+            }
+        };
         // encoder (encoder.py:187-215)
-        URNN_TRY(build_cell(pl, ops, sq, enc[0], p->enc_cell[0], 0, &pl.s[0], nullptr, in[0], out[0], fp));
-        URNN_TRY(build_pool_stem(pl, ops, out[0], 0, pl.s[1], p->enc_stem_w[1], p->enc_stem_b[1], fp));
-        URNN_TRY(build_cell(pl, ops, sq, enc[1], p->enc_cell[1], 1, &pl.s[1], nullptr, in[1], out[1], fp));
-        URNN_TRY(build_pool_stem(pl, ops, out[1], 1, pl.s[2], p->enc_stem_w[2], p->enc_stem_b[2], fp));
-        URNN_TRY(build_cell(pl, ops, sq, enc[2], p->enc_cell[2], 2, &pl.s[2], nullptr, in[2], out[2], fp));
+        URNN_TRY(build_cell(pl, ops, sq, enc[0], p->enc_cell[0], 0, &pl.s[0], nullptr, in[0], out[0], fp)); tag("enc1");
+        URNN_TRY(build_pool_stem(pl, ops, out[0], 0, pl.s[1], p->enc_stem_w[1], p->enc_stem_b[1], fp)); tag("stem2");
+        URNN_TRY(build_cell(pl, ops, sq, enc[1], p->enc_cell[1], 1, &pl.s[1], nullptr, in[1], out[1], fp)); tag("enc2");
+        URNN_TRY(build_pool_stem(pl, ops, out[1], 1, pl.s[2], p->enc_stem_w[2], p->enc_stem_b[2], fp)); tag("stem3");
+        URNN_TRY(build_cell(pl, ops, sq, enc[2], p->enc_cell[2], 2, &pl.s[2], nullptr, in[2], out[2], fp)); tag("enc3");
         // decoder (decoder.py:173-217): deepest first; stage 3 has no x (ConvRNN.py:143-146)
-        URNN_TRY(build_cell(pl, ops, sq, dec[0], p->dec_cell[0], 2, nullptr, &out[2], in[3], out[3], fp));
-        URNN_TRY(build_deconv(pl, ops, out[3], 2, pl.up3, p->dec_stem_w[0], p->dec_stem_b[0], fp));
-        URNN_TRY(build_cell(pl, ops, sq, dec[1], p->dec_cell[1], 1, &pl.up3, &out[1], in[4], out[4], fp));
-        URNN_TRY(build_deconv(pl, ops, out[4], 1, pl.up2, p->dec_stem_w[1], p->dec_stem_b[1], fp));
-        URNN_TRY(build_cell(pl, ops, sq, dec[2], p->dec_cell[2], 0, &pl.up2, &out[0], in[5], out[5], fp));
-        URNN_TRY(build_final_stem(pl, ops, out[5], p->dec_stem_w[2], p->dec_stem_b[2], d->dec_conv[2], fp));
+        URNN_TRY(build_cell(pl, ops, sq, dec[0], p->dec_cell[0], 2, nullptr, &out[2], in[3], out[3], fp)); tag("dec3");
+        URNN_TRY(build_deconv(pl, ops, out[3], 2, pl.up3, p->dec_stem_w[0], p->dec_stem_b[0], fp)); tag("deconv3");
+        URNN_TRY(build_cell(pl, ops, sq, dec[1], p->dec_cell[1], 1, &pl.up3, &out[1], in[4], out[4], fp)); tag("dec2");
+        URNN_TRY(build_deconv(pl, ops, out[4], 1, pl.up2, p->dec_stem_w[1], p->dec_stem_b[1], fp)); tag("deconv2");
+        URNN_TRY(build_cell(pl, ops, sq, dec[2], p->dec_cell[2], 0, &pl.up2, &out[0], in[5], out[5], fp)); tag("dec1");
+        URNN_TRY(build_final_stem(pl, ops, out[5], p->dec_stem_w[2], p->dec_stem_b[2], d->dec_conv[2], fp)); tag("stem_out");
         if (q == 1) {                              // weight images are shared: copy the addresses recorded for parity 0
             size_t gi = 0;
             for (size_t i = 0; i < ops.size(); ++i) if (ops[i].kind == 0) { while (pl.ops[0][gi].kind != 0) ++gi; ops[i].g.P.wimg = pl.ops[0][gi].g.P.wimg; ++gi; }
@@ -483,25 +528,63 @@ static int launch_ew(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStr
 }
 
 // One time step: states of `parity` -> states of `parity ^ 1`, depth/probability maps -> out (2, H, W).
-int step(Plan& pl, int parity, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st) {
+// ev (optional): cudaEvent_t pairs recorded around every launch (stage-1 stem, the program's ops, the head).
+int step(Plan& pl, int parity, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st,
+         cudaEvent_t* ev = nullptr) {
     const urnn_ed_desc& d = pl.d;
+    int evi = 0;
+#define V2_EV() do { if (ev) URNN_CUDA(cudaEventRecord(ev[evi++], st)); } while (0)
+    V2_EV();
     {
         Stem1Args a{x, cin, w, w_ld, b, d.enc_conv[0], d.lrelu_slope, d.H, d.W, d.W / 4, pl.lay.phased, pl.lay.n4p, pl.s[0].ntot, pl.s[0].hi, pl.s[0].lo_off()};
         const long long nthr = (long long)d.H * (d.W / 4);
-        const size_t smem = ((size_t)d.enc_conv[0] * cin + d.enc_conv[0]) * sizeof(float);
+        const size_t smem = (size_t)(((d.enc_conv[0] + 15) / 16) * 16) * (cin + 1) * sizeof(float);
         if (smem > 48 * 1024) { set_error("stage-1 stem: %d x %d weights exceed 48 KB of shared memory", d.enc_conv[0], cin); return URNN_E_UNSUPPORTED; }
         void* args[1] = {(void*)&a};
-        URNN_TRY(launch_ew((const void*)stem1_kernel, dim3((unsigned)((nthr + 127) / 128)), dim3(128), smem, st, args));
+        URNN_TRY(launch_ew((const void*)stem1_kernel, dim3((unsigned)((nthr + 63) / 64)), dim3(64), smem, st, args));
     }
+    V2_EV();
     for (const Op& op : pl.ops[parity]) {
-        if (op.kind == 0) URNN_TRY(launch_gemm(op.g, st));
+        V2_EV();
+        if (op.kind == 0) URNN_TRY(launch_gemm(op.g, st, ev == nullptr));
         else {
             const long long total = (op.b.ntot >> 3) * op.b.F;
             void* args[1] = {(void*)&op.b};
             URNN_TRY(launch_ew((const void*)blend_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, args));
         }
+        V2_EV();
     }
-    return head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, st);
+    V2_EV();
+    URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, st));
+    V2_EV();
+#undef V2_EV
+    return URNN_OK;
+}
+
+// T timed steps: mean milliseconds of every launch (CUDA events on the launching stream), names as "stem1", "enc1.A", ...
+int profile(Plan& pl, int T, const float* inputs, size_t in_elems, int cin, const float* w, long long w_ld, const float* b, float* out,
+            cudaStream_t st, float* op_ms, char* names, int max_ops, int* nops) {
+    const int n = (int)pl.ops[0].size() + 2;
+    if (n > max_ops) { set_error("profile: %d launches > max_ops=%d", n, max_ops); return URNN_E_INVALID; }
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto& e : ev) URNN_CUDA(cudaEventCreate(&e));
+    std::vector<double> acc(n, 0.0);
+    int rc = URNN_OK;
+    for (int t = 0; t < T && rc == URNN_OK; ++t) {
+        rc = step(pl, t & 1, inputs + (size_t)t * in_elems, cin, w, w_ld, b, out, st, ev.data());
+        if (rc != URNN_OK) break;
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("profile: stream synchronisation failed"); rc = URNN_E_CUDA; break; }
+        for (int i = 0; i < n; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]); acc[i] += ms; }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc != URNN_OK) return rc;
+    for (int i = 0; i < n; ++i) {
+        op_ms[i] = (float)(acc[i] / T);
+        const char* nm = i == 0 ? "stem1" : (i == n - 1 ? "head" : pl.ops[0][i - 1].name);
+        snprintf(names + (size_t)i * 24, 24, "%s", nm);
+    }
+    *nops = n;
+    return URNN_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ plan cache (per-step API)
@@ -561,6 +644,10 @@ V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float*
 }
 int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st) {
     return v2::step(*reinterpret_cast<v2::Plan*>(s), t & 1, x, cin, w, w_ld, b, out, st);
+}
+int v2_seq_profile(V2Seq* s, int T, const float* inputs, size_t in_elems, int cin, const float* w, long long w_ld, const float* b, float* out,
+                   cudaStream_t st, float* op_ms, char* names, int max_ops, int* nops) {
+    return v2::profile(*reinterpret_cast<v2::Plan*>(s), T, inputs, in_elems, cin, w, w_ld, b, out, st, op_ms, names, max_ops, nops);
 }
 int v2_seq_end(V2Seq* s, int T, float* const* states, cudaStream_t st) {
     std::unique_ptr<v2::Plan> pl(reinterpret_cast<v2::Plan*>(s));

@@ -111,7 +111,8 @@ static inline int plan_gemm(GemmLaunch& L, int num_sms) {
     if (best < 2) { set_error("gemm_v2: weights %dx%d (hi+lo) leave no room for the operand ring", P.nrows, P.nkb * 64); return URNN_E_UNSUPPORTED; }
     if (const char* e = getenv("URNN_V2_SLOTS")) { const int cap = atoi(e); if (cap >= 2 && cap < best) best = cap; }   // bring-up: ring depth cap
     P.nslots = best;
-    { const char* e = getenv("URNN_V2_L2AHEAD"); P.l2_ahead = e ? atoi(e) : 2; }
+    P.l2_ahead = 0;
+    { const char* e = getenv("URNN_V2_L2HINT"); const int v = e ? atoi(e) : 0; P.l2_hint = v == 1 ? L2_EVICT_FIRST : (v == 2 ? L2_EVICT_LAST : L2_EVICT_NORMAL); }
     L.smem = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total).total;
     const long long ntiles = P.ntot / TILE_M;
     L.grid = (int)(ntiles < num_sms ? ntiles : num_sms);

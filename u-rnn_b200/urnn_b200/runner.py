@@ -115,6 +115,33 @@ class SequenceRunner:
         return depth, prob, [s.clone() for s in st]
 
     @torch.no_grad()
+    def profile_dev(self, inputs, states=None, max_ops=64):
+        """Per-launch mean device time over the T steps of `inputs` (urnn_ed_profile_dev): [(name, milliseconds), ...]."""
+        lib = _capi.load()
+        T = inputs.shape[0]
+        inputs = ops._chk(inputs, "inputs", (T, self.Cin, self.H, self.W))
+        st = self.states[0]
+        for i, dst in enumerate(st):
+            if states is None:
+                dst.zero_()
+            else:
+                dst.copy_(states[i].reshape(dst.shape))
+        need = lib.urnn_ed_sequence_dev_workspace_bytes(C.byref(self.desc))
+        if getattr(self, "_dev_ws", None) is None or self._dev_ws.numel() < need:
+            self._dev_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        ms = (C.c_float * max_ops)()
+        names = C.create_string_buffer(24 * max_ops)
+        n = C.c_int32(0)
+        params = self.net.ed_params()
+        sp = (C.c_void_p * 6)(*[s.data_ptr() for s in st])
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _capi.check(lib.urnn_ed_profile_dev(C.byref(self.desc), C.byref(params), T, C.c_void_p(inputs.data_ptr()), sp,
+                                            C.c_void_p(self._dev_ws.data_ptr()), self._dev_ws.numel(), stream,
+                                            C.cast(ms, C.c_void_p), C.cast(names, C.c_void_p), max_ops, C.cast(C.pointer(n), C.c_void_p)),
+                    "urnn_ed_profile_dev")
+        return [(names.raw[24 * i:24 * i + 24].split(b"\0")[0].decode(), float(ms[i])) for i in range(n.value)]
+
+    @torch.no_grad()
     def run_host(self, inputs_host, out_host=None, states=None):
         """inputs_host (T,Cin,H,W) float32 HOST tensor (pin it for overlap) -> out_host (T,H,W) host tensor with the
         masked depth maps; one call into the C ABI (urnn_ed_sequence_host), which blocks until the last copy landed."""
