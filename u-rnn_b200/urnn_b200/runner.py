@@ -31,12 +31,18 @@ class SequenceRunner:
         self.shapes = state_shapes(H, W, [c.num_features for c in enc_cells], [c.num_features for c in dec_cells])
         dev = self.device
         self.states = [[torch.zeros(s, device=dev) for s in self.shapes] for _ in range(2)]
-        self.ws = torch.empty(ops.ed_workspace_bytes(self.desc), dtype=torch.uint8, device=dev)
+        self._ws = None                      # step workspace of the per-step route, allocated on first use
         self.static_in = torch.zeros((Cin, H, W), device=dev)
         self.static_out = torch.zeros((2, H, W), device=dev)
         self.use_graph = use_graph
         self.graphs = None
         self._params = None
+
+    @property
+    def ws(self):
+        if self._ws is None:
+            self._ws = torch.empty(ops.ed_workspace_bytes(self.desc), dtype=torch.uint8, device=self.device)
+        return self._ws
 
     def _step(self, parity, x, out):
         ops.ed_step_fwd(self.desc, self._params, x, self.states[parity], self.states[parity ^ 1], out, self.ws)
