@@ -1,5 +1,6 @@
-"""Multi-GPU (spatially sharded) == single-GPU, on real GPUs: two processes, one band each, statistics exchanged
-inside the kernels over peer-mapped buffers.  Skipped unless at least 2 CUDA devices are visible."""
+"""Multi-GPU (spatially sharded) == single-GPU, on real GPUs: one process per GPU, one row band each, statistics
+exchanged inside the kernels over peer-mapped buffers.  World sizes 2, 4 and 8 (each skipped unless that many CUDA
+devices are visible); all three arithmetic modes; the 8-rank case runs enough steps to wrap the exchange ring."""
 import os
 import sys
 
@@ -11,10 +12,11 @@ import torch.multiprocessing as mp
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-H, W, HIST, T = 64, 48, 3, 3
+W, HIST = 48, 3
+MODES = ("fp32", "bf16", "f16x3")
 
 
-def _build(Hl, math):
+def _build(Hl, math):   # noqa: E302
     from src.lib.model.networks.model import ED
     from src.lib.model.networks.net_params import get_network_params
     torch.manual_seed(0)
@@ -22,7 +24,7 @@ def _build(Hl, math):
     return ED(False, enc, dec, 0.5, False, input_height=Hl, input_width=W)
 
 
-def _worker(rank, world, port, tmp):
+def _worker(rank, world, port, tmp, H, T):
     sys.path[:0] = [ROOT, os.path.join(ROOT, "u-rnn_b200")]
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -35,7 +37,7 @@ def _worker(rank, world, port, tmp):
     xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, HIST))
     r0, rows = ud.band(H, world, rank)
     errs = {}
-    for math in ("fp32", "bf16"):
+    for math in MODES:
         full_sd = _build(H, math).state_dict()
         net = _build(rows, math)
         net.load_state_dict(ud.shard_state_dict(full_sd, world, rank), strict=True)
@@ -52,25 +54,32 @@ def _worker(rank, world, port, tmp):
         for i, c in enumerate(sc):
             e = max(e, float(np.abs(st[i].cpu().numpy()[0] - ref[f"state{i}"][:, r0 // c:(r0 + rows) // c]).max()))
         errs[math] = e
-    np.save(os.path.join(tmp, f"err{rank}.npy"), np.array([errs["fp32"], errs["bf16"]]))
+    np.save(os.path.join(tmp, f"err{rank}.npy"), np.array([errs[m] for m in MODES]))
     ud.shutdown_spatial_sharding()
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_bands_equal_single_gpu(tmp_path):
+@pytest.mark.parametrize("world,T", [(2, 3), (4, 3), (8, 6)])
+def test_bands_equal_single_gpu(tmp_path, world, T):
+    """T steps on a (32 * world) x 48 grid: `world` bands of 32 rows vs the same grid on one GPU.  Every step issues 17
+    statistic exchanges, so T = 6 (102 exchanges) wraps the 64-entry exchange ring of the communicator."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     from oracle import urnn_oracle as O
+    H = 32 * world
     xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, HIST)).cuda()
-    for math in ("fp32", "bf16"):
+    for math in MODES:
         net = _build(H, math).cuda().eval()
         st = [torch.zeros(1, *s.shape, device="cuda") for s in O.zero_states(H, W)]
         with torch.no_grad():
             for t in range(T):
                 out, *st = net(xs[t][None, None], *st)
         np.savez(tmp_path / f"ref_{math}.npz", **{f"state{i}": s.cpu().numpy()[0] for i, s in enumerate(st)})
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    for r in range(2):
+        del net
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, str(tmp_path), H, T), nprocs=world, join=True)
+    for r in range(world):
         e = np.load(tmp_path / f"err{r}.npy")
         assert e[0] < 1e-5, e          # fp32: only the summation order of the statistics differs
         assert e[1] < 2e-2, e          # bf16: rounding flips at bf16 boundaries, same bound as the single-GPU tests
+        assert e[2] < 2e-5, e          # f16x3: split products + merge order of the statistics

@@ -590,7 +590,7 @@ int profile(Plan& pl, int T, const float* inputs, size_t in_elems, int cin, cons
 // ------------------------------------------------------------------------------------------------ plan cache (per-step API)
 // urnn_ed_step_fwd is called once per time step by the drop-in ED.forward; building a plan (20 tensor maps, launch
 // planning) costs ~0.1 ms of host time, so the last few plans are kept, keyed by everything they depend on.
-struct CacheKey { int device; urnn_ed_desc d; urnn_ed_params p; void* ws; size_t ws_bytes; };
+struct CacheKey { int device; urnn_ed_desc d; urnn_ed_params p; void* ws; size_t ws_bytes; int comm_world, comm_rank; void* comm_seq; };
 static bool same_key(const CacheKey& a, const CacheKey& b) { return memcmp(&a, &b, sizeof(CacheKey)) == 0; }
 struct CacheEnt { CacheKey key; std::unique_ptr<Plan> plan; unsigned long long stamp; };
 static std::mutex g_cache_mu;
@@ -601,6 +601,7 @@ static int cached_plan(const urnn_ed_desc* d, const urnn_ed_params* p, void* ws,
     CacheKey key; memset(&key, 0, sizeof(key));
     URNN_CUDA(cudaGetDevice(&key.device));
     key.d = *d; key.p = *p; key.ws = ws; key.ws_bytes = ws_bytes;
+    { CommDev c; current_comm(&c); key.comm_world = c.world; key.comm_rank = c.rank; key.comm_seq = c.seq; }   // plans embed the communicator
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (CacheEnt& e : g_cache) if (same_key(e.key, key)) { e.stamp = ++g_stamp; *out = e.plan.get(); return URNN_OK; }
     std::unique_ptr<Plan> pl(new Plan());
