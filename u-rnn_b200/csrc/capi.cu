@@ -38,7 +38,7 @@ static int check_cell(const urnn_cell_desc* d, const urnn_cell_params* p, const 
 static CommDev g_comm = {1, 0, {nullptr}, {nullptr}, nullptr};
 static void* g_comm_local = nullptr;
 static void* g_comm_peer[COMM_MAX_WORLD] = {nullptr};
-static const size_t kSlotBytes = (size_t)COMM_RING * COMM_MAX_WORLD * COMM_MAX_SETS * sizeof(double4);
+static const size_t kSlotBytes = (size_t)COMM_RING * COMM_MAX_WORLD * COMM_MAX_SETS * COMM_WORDS * sizeof(unsigned long long);
 static const size_t kFlagBytes = (size_t)COMM_RING * COMM_MAX_WORLD * sizeof(unsigned);
 static const size_t kCommBytes = kSlotBytes + kFlagBytes + 256;
 
@@ -630,7 +630,7 @@ int urnn_comm_local_init(int32_t world, int32_t rank, void* handle_out) {
     g_comm.seq = (unsigned*)((char*)g_comm_local + kSlotBytes + kFlagBytes);
     // remember the intended world in the (still inactive) communicator through the peer table size
     for (int r = 0; r < COMM_MAX_WORLD; ++r) if (r != rank) g_comm_peer[r] = nullptr;
-    g_comm.slots[rank] = (double4*)g_comm_local;
+    g_comm.slots[rank] = (unsigned long long*)g_comm_local;
     g_comm.flags[rank] = (unsigned*)((char*)g_comm_local + kSlotBytes);
     // world is stored negated until connected
     g_comm.world = -world;
@@ -647,7 +647,7 @@ int urnn_comm_connect(const void* all_handles) {
         void* ptr = nullptr;
         URNN_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         g_comm_peer[r] = ptr;
-        g_comm.slots[r] = (double4*)ptr;
+        g_comm.slots[r] = (unsigned long long*)ptr;
         g_comm.flags[r] = (unsigned*)((char*)ptr + kSlotBytes);
     }
     g_comm.world = world;

@@ -32,7 +32,7 @@ constexpr int NWARP_EPI = 16;                 // plain launches: 16 epilogue war
 constexpr int NWARP_EPI_GATED = 8, NWARP_GATE = 12;
 constexpr int EPI_WARP0 = 4;
 constexpr int NTHREADS_PLAIN = 32 * (EPI_WARP0 + NWARP_EPI), NTHREADS_GATED = 32 * (EPI_WARP0 + NWARP_EPI_GATED + NWARP_GATE);
-constexpr size_t SMEM_MAX = 231424;       // 227 KB opt-in limit minus 1 KB for static shared memory
+constexpr size_t SMEM_MAX = 229376;       // 227 KB opt-in limit minus 3 KB for static shared memory (exchange staging)
 
 enum { EPI_STATS_F32 = 0, EPI_LRELU_SPLIT = 1, EPI_LRELU_F32 = 2 };
 enum { ACC_SINGLE = 0, ACC_POOL = 1, ACC_DECONV = 2 };
@@ -58,36 +58,32 @@ __device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, 
     n = nn;
 }
 
-// One-shot all-reduce of the (mean, M2, n) triples over NVLink peer memory (same protocol as stats_exchange).
+// One-shot all-reduce of the (mean, M2, n) triples over NVLink peer memory (ll_allgather, urnn_common.cuh), merged in
+// rank order with Chan's formula: every rank obtains bit-identical totals.
 __device__ __forceinline__ void stats2_exchange(const StatSink2& s) {
     const CommDev& c = s.comm;
     if (c.world <= 1) return;
-    __shared__ unsigned sh_seq;
-    if (threadIdx.x == 0) sh_seq = *c.seq;
-    __syncthreads();
-    const unsigned seq = sh_seq, ring = seq % COMM_RING, epoch = seq / COMM_RING + 1;
-    const int slot0 = (int)(ring * c.world + c.rank) * COMM_MAX_SETS;
-    for (int i = threadIdx.x; i < c.world * s.nsets; i += blockDim.x) {
-        const int peer = i / s.nsets, set = i % s.nsets;
-        c.slots[peer][slot0 + set] = make_double4(s.total[4 * set], s.total[4 * set + 1], s.total[4 * set + 2], 0.0);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + ring * c.world + c.rank, epoch);
-    if (threadIdx.x < c.world) {
-        const unsigned* f = c.flags[c.rank] + ring * c.world + threadIdx.x;
-        while (ld_acquire_sys(f) != epoch) { __nanosleep(64); }
+    __shared__ unsigned xin[COMM_MAX_SETS * 6], xout[COMM_MAX_WORLD * COMM_MAX_SETS * 6];
+    if (threadIdx.x < s.nsets) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const unsigned long long v = (unsigned long long)__double_as_longlong(s.total[4 * threadIdx.x + k]);
+            xin[6 * threadIdx.x + 2 * k] = (unsigned)v; xin[6 * threadIdx.x + 2 * k + 1] = (unsigned)(v >> 32);
+        }
     }
     __syncthreads();
+    ll_allgather(c, xin, s.nsets, 6, xout);
     if (threadIdx.x < s.nsets) {
         double n = 0.0, mean = 0.0, m2 = 0.0;
         for (int r = 0; r < c.world; ++r) {
-            const volatile double4* src = c.slots[c.rank] + (int)(ring * c.world + r) * COMM_MAX_SETS + threadIdx.x;
-            chan_merge(n, mean, m2, src->z, src->x, src->y);
+            const unsigned* w = xout + (r * s.nsets + threadIdx.x) * 6;
+            double t[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[k] = __longlong_as_double((long long)((unsigned long long)w[2 * k] | ((unsigned long long)w[2 * k + 1] << 32)));
+            chan_merge(n, mean, m2, t[2], t[0], t[1]);
         }
         s.total[4 * threadIdx.x] = mean; s.total[4 * threadIdx.x + 1] = m2; s.total[4 * threadIdx.x + 2] = n;
     }
-    if (threadIdx.x == 0) *c.seq = seq + 1;
     __syncthreads();
 }
 

@@ -79,10 +79,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 constexpr int COMM_MAX_WORLD = 8;
 constexpr int COMM_RING = 64;        // exchanges in flight are at most 1 apart between ranks; the ring avoids resets
 constexpr int COMM_MAX_SETS = 8;     // statistics sets per exchange (<= 8 GroupNorm groups / 2 LayerNorms)
+constexpr int COMM_WORDS = 8;        // 32-bit payload words per set (6 used: three doubles)
 struct CommDev {
     int world, rank;                               // world <= 1: no exchange
-    double4*  slots[COMM_MAX_WORLD];               // peer p: slots[p][(ring*world + src_rank)*COMM_MAX_SETS + set]
-    unsigned* flags[COMM_MAX_WORLD];               // peer p: flags[p][ring*world + src_rank] = epoch
+    unsigned long long* slots[COMM_MAX_WORLD];     // peer p: slots[p][((ring*world + src_rank)*COMM_MAX_SETS + set)*COMM_WORDS + word]
+    unsigned* flags[COMM_MAX_WORLD];               // (unused by the LL protocol; kept in the buffer layout)
     unsigned* seq;                                 // local exchange counter (device memory)
 };
 
@@ -95,13 +96,39 @@ struct StatSink {
     CommDev   comm;      // cross-GPU exchange of the totals (world <= 1: none)
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// One-shot all-gather of `nw` 32-bit words per set from every rank, "LL" style: every 8-byte store carries 4 bytes of
+// payload and the 4-byte epoch of this exchange, so a word is valid as soon as its epoch matches -- one NVLink hop, no
+// system fence, no separate flag (the fence + flag round trip was ~2/3 of the exposed exchange latency).  The epoch grows
+// with every wrap of the ring, so stale words never match.  Called by all threads of ONE CTA.
+//   in : words_in[set*nw + w]           (shared or global memory of this CTA)
+//   out: words_out[(r*nsets + set)*nw + w] for every rank r (shared memory, >= world*nsets*nw words)
+__device__ __forceinline__ void ll_allgather(const CommDev& c, const unsigned* words_in, int nsets, int nw, unsigned* words_out) {
+    __shared__ unsigned sh_seq;
+    if (threadIdx.x == 0) sh_seq = *c.seq;
+    __syncthreads();
+    const unsigned seq = sh_seq, ring = seq % COMM_RING, epoch = seq / COMM_RING + 1;
+    const int per_rank = nsets * nw;
+    // 1. my words -> slot `rank` of every rank (including myself)
+    for (int i = threadIdx.x; i < c.world * per_rank; i += blockDim.x) {
+        const int peer = i / per_rank, j = i - peer * per_rank, set = j / nw, w = j - set * nw;
+        unsigned long long* dst = c.slots[peer] + ((size_t)(ring * c.world + c.rank) * COMM_MAX_SETS + set) * COMM_WORDS + w;
+        const unsigned long long v = (unsigned long long)words_in[j] | ((unsigned long long)epoch << 32);
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+    }
+    // 2. every rank's words from MY buffer
+    for (int i = threadIdx.x; i < c.world * per_rank; i += blockDim.x) {
+        const int r = i / per_rank, j = i - r * per_rank, set = j / nw, w = j - set * nw;
+        const unsigned long long* src = c.slots[c.rank] + ((size_t)(ring * c.world + r) * COMM_MAX_SETS + set) * COMM_WORDS + w;
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if ((unsigned)(v >> 32) == epoch) break;
+            __nanosleep(32);
+        }
+        words_out[i] = (unsigned)v;
+    }
+    if (threadIdx.x == 0) *c.seq = seq + 1;
+    __syncthreads();
 }
 
 // One-shot all-reduce of s.total[0..nsets) across ranks; called by all threads of the last CTA after the local
@@ -109,35 +136,24 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void stats_exchange(const StatSink& s) {
     const CommDev& c = s.comm;
     if (c.world <= 1) return;
-    __shared__ unsigned sh_seq;
-    if (threadIdx.x == 0) sh_seq = *c.seq;
-    __syncthreads();
-    const unsigned seq = sh_seq, ring = seq % COMM_RING, epoch = seq / COMM_RING + 1;
-    const int slot0 = (int)(ring * c.world + c.rank) * COMM_MAX_SETS;
-    // 1. my totals -> slot `rank` of every rank (including myself)
-    for (int i = threadIdx.x; i < c.world * s.nsets; i += blockDim.x) {
-        const int peer = i / s.nsets, set = i % s.nsets;
-        c.slots[peer][slot0 + set] = make_double4(s.total[set].x, s.total[set].y, 0.0, 0.0);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + ring * c.world + c.rank, epoch);
-    // 2. wait until every rank has published this exchange into MY buffer
-    if (threadIdx.x < c.world) {
-        const unsigned* f = c.flags[c.rank] + ring * c.world + threadIdx.x;
-        while (ld_acquire_sys(f) != epoch) { __nanosleep(64); }
+    __shared__ unsigned xin[COMM_MAX_SETS * 4], xout[COMM_MAX_WORLD * COMM_MAX_SETS * 4];
+    if (threadIdx.x < s.nsets) {
+        const double2 t = s.total[threadIdx.x];
+        const unsigned long long a = (unsigned long long)__double_as_longlong(t.x), b = (unsigned long long)__double_as_longlong(t.y);
+        xin[4 * threadIdx.x] = (unsigned)a; xin[4 * threadIdx.x + 1] = (unsigned)(a >> 32);
+        xin[4 * threadIdx.x + 2] = (unsigned)b; xin[4 * threadIdx.x + 3] = (unsigned)(b >> 32);
     }
     __syncthreads();
-    // 3. sum in rank order
+    ll_allgather(c, xin, s.nsets, 4, xout);
     if (threadIdx.x < s.nsets) {
         double a = 0.0, b = 0.0;
         for (int r = 0; r < c.world; ++r) {
-            const volatile double4* src = c.slots[c.rank] + (int)(ring * c.world + r) * COMM_MAX_SETS + threadIdx.x;
-            a += src->x; b += src->y;
+            const unsigned* w = xout + (r * s.nsets + threadIdx.x) * 4;
+            a += __longlong_as_double((long long)((unsigned long long)w[0] | ((unsigned long long)w[1] << 32)));
+            b += __longlong_as_double((long long)((unsigned long long)w[2] | ((unsigned long long)w[3] << 32)));
         }
         s.total[threadIdx.x] = make_double2(a, b);
     }
-    if (threadIdx.x == 0) *c.seq = seq + 1;
     __syncthreads();
 }
 
