@@ -267,9 +267,12 @@ def test_sequence_host_entry_point():
             assert torch.equal(a, b)
 
 
-def test_event_entry_point_equals_dense_inputs():
+@pytest.mark.parametrize("math", ["fp32", "f16x3"])
+def test_event_entry_point_equals_dense_inputs(math):
     """urnn_ed_event_host (raw maps + scalar rainfall series, rainfall folded into a per-step stage-1 bias) reproduces
-    the dense-input loop built with the reference's preprocess_inputs recipe (fp32: summation order only)."""
+    the dense-input loop built with the reference's preprocess_inputs recipe (summation order only).  The recipe
+    (oracle.synthetic_event_inputs) is pinned to the reference's Dynamic2DFlood.preprocess_inputs by
+    tests/test_callers_golden.py."""
     from urnn_b200.runner import SequenceRunner
     H, W, hist, T = 24, 40, 3, 7
     rng = np.random.RandomState(42)                  # same draws as O.synthetic_event_inputs
@@ -278,9 +281,9 @@ def test_event_entry_point_equals_dense_inputs():
     manhole = (rng.rand(H, W) > 0.95).astype(np.float64)
     rain = rng.rand(T) * 30.0
     xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, hist)).to(DEV)
-    net = build_ed(H, W, 2 * hist + 3)
+    net = build_ed(H, W, 2 * hist + 3, math=math)
     runner = SequenceRunner(net, H, W, 2 * hist + 3, use_graph=False)
-    depth, _, final = runner.run(xs)
+    depth, _, final = runner.run_dev(xs)
     f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
     rain32 = f32(rain)
     out_host, final_e = runner.run_event_host(f32(dem), f32(imperv), f32(manhole), rain32, torch.cumsum(rain32, 0), hist, 60.0, 250.0)
