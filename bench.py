@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default=os.environ.get("URNN_MATH", "f16x3"), choices=["fp32", "bf16", "f16x3"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: BASELINE config 4 -- one step = one SWP window (seq_num time steps forward with autograd, backward, "
+                         "gradient all-reduce, clip, Adam), fp32 kernels")
+    ap.add_argument("--seq-num", type=int, default=12, help="--mode train: time steps per window (location1_scratch.yaml:56)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = every rank owns an H x W band of an (N*H) x W grid; strong = the H x W grid is split into N bands")
     ap.add_argument("--height", type=int, default=H_DEF)
@@ -425,6 +429,80 @@ def run_ours(a):
     shutdown(dist)
 
 
+def run_train(a):
+    """BASELINE config 4: SWP training windows at the location1 grid.  One "step" = one window: seq_num time steps forward
+    through the drop-in modules with autograd (main.py:674-684), loss, backward (recompute-in-backward CUDA kernels, fp32),
+    all-reduce of the replicated weight gradients + global clip norm when sharded (main.py:756-761), Adam step."""
+    from urnn_b200 import _capi, ops
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        from urnn_b200 import dist as ud
+        dist.init_process_group("nccl", device_id=dev)
+        ud.init_spatial_sharding()
+    from urnn_b200 import dist as ud
+    ops.set_default_math("fp32")
+    hist = a.hist; C = 2 * hist + 3; H, W = a.height, a.width; S = a.seq_num
+    net = build_net(H, W, C, "fp32", dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=0.01)
+    xs = device_inputs(S, C, H, W, hist, dev)
+    torch.manual_seed(7 + rank)
+    label = torch.rand(S, H, W, device=dev) * 0.3
+    label[label < 0.25] = 0
+    lib = _capi.load()
+
+    def window():
+        opt.zero_grad(set_to_none=True)
+        st = [torch.zeros(s, device=dev) for s in state_shapes(H, W)]
+        regs = []
+        for t in range(S):
+            out, *st = net(xs[t][None, None], *st)
+            regs.append(out)
+        reg = torch.cat(regs, dim=1)[0]
+        wet = (label > 0).float()
+        loss = (((reg - label) ** 2) * (1.0 + 19.0 * wet)).sum() / (S * H * W * world)      # WMSE-style weighting, global normalisation
+        loss.backward()
+        if world > 1:
+            ud.allreduce_window_gradients(net)
+            ud.clip_grad_norm_sharded(net, 1.0)
+        else:
+            torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(max(1, a.warmup)):
+        window()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier(); torch.cuda.synchronize()
+    n0 = lib.urnn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
+        e0.record()
+        for _ in range(a.steps):
+            loss = window()
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(); torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    if dist is not None:
+        t = torch.tensor([sec], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); sec = float(t.item())
+    if rank == 0:
+        emit({"metric": "grid-cells*steps/s (SWP window: fwd + bwd + grad all-reduce + clip + Adam)", "mode": "train",
+              "value": world * H * W * S * a.steps / sec, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+              "ms_per_step": sec / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": f"location1 SWP training window: {world * H}x{W}" + (f" ({world} row bands)" if world > 1 else "") +
+                                     f", C_in={C}, seq_num={S}, Adam lr 0.01, grad_clip 1.0, weighted-MSE loss",
+                         "sharding": "row bands; in-kernel NVLink statistic exchange (fwd + bwd), NCCL all-reduce of 420146 replicated gradients per window" if world > 1 else "none",
+                         "published": "README.md:626 (RTX 4090, derived): ~1.7 M cells*steps/s fwd+bwd"},
+              "gpu_launches": int(lib.urnn_launch_count() - n0), "clocks": clk.summary(), "loss": float(loss)})
+    shutdown(dist)
+
+
 def shutdown(dist):
     if dist is not None:
         from urnn_b200 import dist as ud
@@ -496,6 +574,8 @@ def main():
         _REDIRECT = StdoutToStderr()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.mode == "train":
+        run_train(a)
     else:
         run_ours(a)
 

@@ -121,10 +121,15 @@ cell_bwd_e1_kernel(const float* __restrict__ G, const float* __restrict__ C, con
 
 // per-channel sums -> parameter gradients and per-group GroupNorm-backward coefficients (one block)
 //   dgamma[c] += B_c, dbeta[c] += A_c;  m1[g] = sum_c gamma_c A_c / n,  m2[g] = sum_c gamma_c B_c / n
+// Spatial sharding: the per-group sums run over the whole grid, so they are all-gathered over NVLink (ll_allgather) and
+// added in rank order; `count` is the global element count.  dgamma / dbeta stay rank-local partial sums (the caller
+// all-reduces the gradients of replicated parameters once per window).
 __global__ void gn_bwd_coef_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, float* __restrict__ dgamma,
-                                   float* __restrict__ dbeta, float2* __restrict__ coef, int channels, double count) {
+                                   float* __restrict__ dbeta, float2* __restrict__ coef, int channels, double count, CommDev comm) {
     __shared__ double s1[8], s2[8];
+    __shared__ unsigned xin[8 * 4], xout[COMM_MAX_WORLD * 8 * 4];
     const int c = threadIdx.x;
+    const int ngroups = channels >> 5;
     if (c < 8) { s1[c] = 0.0; s2[c] = 0.0; }
     __syncthreads();
     if (c < channels) {
@@ -135,7 +140,46 @@ __global__ void gn_bwd_coef_kernel(const double* __restrict__ sums, const float*
         atomicAdd(&s2[c >> 5], (double)gamma[c] * B);
     }
     __syncthreads();
-    if (c < (channels >> 5)) coef[c] = make_float2((float)(s1[c] / count), (float)(s2[c] / count));
+    if (comm.world > 1) {
+        if (c < ngroups) {
+            const unsigned long long a = (unsigned long long)__double_as_longlong(s1[c]), b = (unsigned long long)__double_as_longlong(s2[c]);
+            xin[4 * c] = (unsigned)a; xin[4 * c + 1] = (unsigned)(a >> 32); xin[4 * c + 2] = (unsigned)b; xin[4 * c + 3] = (unsigned)(b >> 32);
+        }
+        __syncthreads();
+        ll_allgather(comm, xin, ngroups, 4, xout);
+        if (c < ngroups) {
+            double a = 0.0, b = 0.0;
+            for (int r = 0; r < comm.world; ++r) {
+                const unsigned* w = xout + (r * ngroups + c) * 4;
+                a += __longlong_as_double((long long)((unsigned long long)w[0] | ((unsigned long long)w[1] << 32)));
+                b += __longlong_as_double((long long)((unsigned long long)w[2] | ((unsigned long long)w[3] << 32)));
+            }
+            s1[c] = a; s2[c] = b;
+        }
+        __syncthreads();
+    }
+    if (c < ngroups) coef[c] = make_float2((float)(s1[c] / count), (float)(s2[c] / count));
+}
+
+// in-place sum over the ranks of `nsets` groups of two doubles (LayerNorm backward sums of the head); one block
+__global__ void comm_sum2_kernel(double* __restrict__ v, int nsets, CommDev comm) {
+    __shared__ unsigned xin[8 * 4], xout[COMM_MAX_WORLD * 8 * 4];
+    const int c = threadIdx.x;
+    if (c < nsets) {
+        const unsigned long long a = (unsigned long long)__double_as_longlong(v[2 * c]), b = (unsigned long long)__double_as_longlong(v[2 * c + 1]);
+        xin[4 * c] = (unsigned)a; xin[4 * c + 1] = (unsigned)(a >> 32); xin[4 * c + 2] = (unsigned)b; xin[4 * c + 3] = (unsigned)(b >> 32);
+    }
+    __syncthreads();
+    ll_allgather(comm, xin, nsets, 4, xout);
+    if (c < nsets) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < comm.world; ++r) {
+            const unsigned* w = xout + (r * nsets + c) * 4;
+            a += __longlong_as_double((long long)((unsigned long long)w[0] | ((unsigned long long)w[1] << 32)));
+            b += __longlong_as_double((long long)((unsigned long long)w[2] | ((unsigned long long)w[3] << 32)));
+        }
+        v[2 * c] = a; v[2 * c + 1] = b;
+    }
 }
 
 // dX = rstd * (gamma*dy - m1 - xhat*m2), in place over the dy map; X is the pre-normalisation map
@@ -207,12 +251,12 @@ int cgru_bwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     const int Keff = Cx_eff + Ch;
     const long aoff = x ? 0 : d->Cx;
     CommDev comm; current_comm(&comm);
-    if (comm.world > 1) { set_error("cgru_bwd: spatially sharded backward is not implemented"); return URNN_E_UNSUPPORTED; }
+    if (F > 128) { set_error("cgru_bwd: num_features=%d > 128 is not supported (8 GroupNorm groups per statistics exchange)", F); return URNN_E_UNSUPPORTED; }
     CellBwdWs w;
     size_t need = cell_bwd_layout(d, ws, ws_bytes, &w);
     if (need > ws_bytes) { set_error("cgru_bwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
     if (dh == nullptr) dh = w.dh_scratch;
-    const double count = 32.0 * (double)N;
+    const double count = 32.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);      // GroupNorm spans the whole (sharded) grid
 
     // ---- recompute the forward sweeps: G, C, folded affines, statistics
     CellWsView f;
@@ -229,7 +273,7 @@ int cgru_bwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
                                               w.DC, w.DY1, w.sums2, w.sums1, N);
     URNN_LAUNCH_CHECK();
     // ---- GroupNorm-2 backward -> dC
-    gn_bwd_coef_kernel<<<1, 256, 0, st>>>(w.sums2, p->gn2_w, gr ? gr->gn2_w : nullptr, gr ? gr->gn2_b : nullptr, w.coef2, F, count);
+    gn_bwd_coef_kernel<<<1, 256, 0, st>>>(w.sums2, p->gn2_w, gr ? gr->gn2_w : nullptr, gr ? gr->gn2_b : nullptr, w.coef2, F, count, comm);
     URNN_LAUNCH_CHECK();
     gn_bwd_apply_kernel<<<gridF, 256, 0, st>>>(w.DC, f.C, p->gn2_w, w.st2, w.coef2, N); URNN_LAUNCH_CHECK();
     // ---- candidate conv backward: dW2 += dC [x|e|r*h]^T ; d[x|e|r*h] = W2^T dC
@@ -261,7 +305,7 @@ int cgru_bwd_fp32(const urnn_cell_desc* d, const urnn_cell_params* p, const floa
     // ---- E3: reset-gate backward; GroupNorm-1 backward -> dG
     cell_bwd_e3_kernel<<<gridF, 256, 0, st>>>(f.G, h, w.DRH, f.scale1, f.shift1, w.st1, dh, w.DY1, w.sums1, F, N);
     URNN_LAUNCH_CHECK();
-    gn_bwd_coef_kernel<<<1, 256, 0, st>>>(w.sums1, p->gn1_w, gr ? gr->gn1_w : nullptr, gr ? gr->gn1_b : nullptr, w.coef1, 2 * F, count);
+    gn_bwd_coef_kernel<<<1, 256, 0, st>>>(w.sums1, p->gn1_w, gr ? gr->gn1_w : nullptr, gr ? gr->gn1_b : nullptr, w.coef1, 2 * F, count, comm);
     URNN_LAUNCH_CHECK();
     gn_bwd_apply_kernel<<<grid2F, 256, 0, st>>>(w.DY1, f.G, p->gn1_w, w.st1, w.coef1, N); URNN_LAUNCH_CHECK();
     // ---- gate conv backward: dW1 += dG [x|e|h]^T ; d[x|e|h] += W1^T dG
@@ -301,7 +345,6 @@ size_t head_bwd_workspace(int H, int W) { return head_bwd_layout(H, W, nullptr, 
 int head_bwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p, const float* feat,
                   const float* dout, float* dfeat, const urnn_head_grads* g, void* ws, size_t ws_bytes, cudaStream_t st) {
     CommDev comm; current_comm(&comm);
-    if (comm.world > 1) { set_error("head_bwd: spatially sharded backward is not implemented"); return URNN_E_UNSUPPORTED; }
     HeadBwdWs w;
     size_t need = head_bwd_layout(H, W, ws, ws_bytes, &w);
     if (need > ws_bytes) { set_error("head_bwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
@@ -311,7 +354,7 @@ int head_bwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, cons
     URNN_CUDA(cudaMemsetAsync(w.psum, 0, 40 * sizeof(double), st));
     HeadBwdDev hb;
     hb.fwd.p = *p; hb.fwd.cls_thred = cls_thred; hb.fwd.eps = ln_eps; hb.fwd.slope = slope; hb.fwd.plane = N;
-    hb.fwd.count = 16.0 * (double)N;
+    hb.fwd.count = 16.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);     // LayerNorm([16,H,W]) over the whole (sharded) grid
     hb.fwd.sink = StatSink{w.partial, w.total, w.counter, 5, w.gx, comm};
     hb.g = *g; hb.bsum = w.bsum; hb.psum = w.psum; hb.dout = dout; hb.dfeat = dfeat;
     hb.m0 = w.m[0]; hb.m1 = w.m[1]; hb.m2 = w.m[2]; hb.m3 = w.m[3];
@@ -321,11 +364,14 @@ int head_bwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, cons
     head_kernel<2><<<w.gx, 128, 0, st>>>(hb.fwd, feat, nullptr, (int)N); URNN_LAUNCH_CHECK();
     // backward sweeps
     head_bwd_kernel<1><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();
+    if (comm.world > 1) { comm_sum2_kernel<<<1, 64, 0, st>>>(w.bsum + 2 * 3, 2, comm); URNN_LAUNCH_CHECK(); }      // LayerNorm sets 3, 4
     head_pred_grads_kernel<<<1, 32, 0, st>>>(w.psum, *g); URNN_LAUNCH_CHECK();
     head_bwd_kernel<2><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();
+    if (comm.world > 1) { comm_sum2_kernel<<<1, 64, 0, st>>>(w.bsum + 2 * 1, 2, comm); URNN_LAUNCH_CHECK(); }      // sets 1, 2
     URNN_TRY(launch_wgrad(w.m[0], N, 16, 16, (int)N, single_map_loader(w.m[1], 16, N), g->conv_w[2], 16, 1, nullptr, 0, st));   // cls_convs.1
     URNN_TRY(launch_wgrad(w.m[2], N, 16, 16, (int)N, single_map_loader(w.m[3], 16, N), g->conv_w[4], 16, 1, nullptr, 0, st));   // reg_convs.1
     head_bwd_kernel<3><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();
+    if (comm.world > 1) { comm_sum2_kernel<<<1, 64, 0, st>>>(w.bsum, 1, comm); URNN_LAUNCH_CHECK(); }               // set 0
     URNN_TRY(launch_wgrad(w.m[0], N, 16, 16, (int)N, single_map_loader(w.m[1], 16, N), g->conv_w[1], 16, 1, nullptr, 0, st));   // cls_convs.0
     URNN_TRY(launch_wgrad(w.m[2], N, 16, 16, (int)N, single_map_loader(w.m[1], 16, N), g->conv_w[3], 16, 1, nullptr, 0, st));   // reg_convs.0
     head_bwd_kernel<4><<<w.gx, 128, 0, st>>>(hb, feat, (int)N); URNN_LAUNCH_CHECK();

@@ -68,3 +68,51 @@ def shutdown_spatial_sharding(group=None):
     if dist.is_initialized():
         dist.barrier(group)
     _capi.load().urnn_comm_destroy()
+
+
+# ---- training under spatial sharding (SURVEY.md 8e "Collectives -- backward") -----------------------------------------
+def _is_sharded(name, p):
+    """LayerNorm([16,H,W]) affine maps of the head live with the rows of their band; everything else is replicated."""
+    return ".ln." in name and p.dim() == 3
+
+
+def allreduce_window_gradients(net, group=None):
+    """After loss.backward() on every rank's band: sum the gradients of the REPLICATED parameters over the ranks with one
+    flattened all-reduce (420 146 floats = 1.7 MB for the published architecture; NCCL over NVLink).  The in-kernel
+    statistic exchanges already made every rank's backward see the whole grid; what is left is the sum over pixels of the
+    weight gradients.  Gradients of the sharded LayerNorm maps stay local.  The loss must be normalised by the GLOBAL
+    number of elements (e.g. band mean / world) so that the summed gradient is the gradient of the global loss."""
+    named = [(n, p) for n, p in net.named_parameters() if p.grad is not None and not _is_sharded(n, p)]
+    if not named or dist.get_world_size(group) == 1:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1) for _, p in named])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for _, p in named:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    return flat.numel()
+
+
+def clip_grad_norm_sharded(net, max_norm, group=None, eps=1e-6):
+    """torch.nn.utils.clip_grad_norm_ (main.py:759-761) when the LayerNorm maps are sharded: the global 2-norm is
+    sqrt(|replicated grads|^2 + sum over ranks |local sharded grads|^2) -- one scalar all-reduce."""
+    rep = torch.zeros((), device=next(net.parameters()).device, dtype=torch.float64)
+    loc = torch.zeros_like(rep)
+    for n, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        s = p.grad.double().pow(2).sum()
+        if _is_sharded(n, p):
+            loc += s
+        else:
+            rep += s
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(loc, op=dist.ReduceOp.SUM, group=group)
+    total = torch.sqrt(rep + loc)
+    coef = torch.clamp(max_norm / (total + eps), max=1.0).float()
+    for p in net.parameters():
+        if p.grad is not None:
+            p.grad.mul_(coef)
+    return total.float()
