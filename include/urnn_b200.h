@@ -17,6 +17,10 @@
  *   - Return value: 0 on success, a negative URNN_E_* code otherwise; urnn_last_error() returns a
  *     thread-local message for the last failing call on this thread.
  *   - Inputs are never modified.  Outputs are fully overwritten.
+ *   - Devices / threads: every call acts on the CUDA device that is current on the calling thread; nothing is cached per
+ *     process (function attributes are set per launch, copy streams of the *_host entry points exist once per device,
+ *     launch plans of urnn_ed_step_fwd are cached per (device, descriptor, parameter block, workspace, communicator)).
+ *     The spatial-sharding communicator (urnn_comm_*) is the one process-wide object: one process drives one GPU.
  */
 #ifndef URNN_B200_H
 #define URNN_B200_H
@@ -198,6 +202,11 @@ size_t urnn_ed_sequence_dev_workspace_bytes(const urnn_ed_desc* d);
 int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T,
                          const float* inputs_dev, float* out_dev, float* prob_dev, float* const* states,
                          void* ws, size_t ws_bytes, void* stream);
+
+/* Host-only helper (no GPU work): position of pixel (y, x) of the level-`level` map (0: H x W, 1: H/2 x W/2, 2: H/4 x W/4)
+ * inside a channel plane of the library's internal phase-separated layout (URNN_MATH_F16X3), and the
+ * padded plane size in *plane_elems.  Returns -1 for an invalid request.  Used by the tests to pin the layout. */
+int64_t urnn_layout_index(int32_t H, int32_t W, int32_t level, int32_t y, int32_t x, int64_t* plane_elems);
 
 /* Measurement entry point (URNN_MATH_F16X3): T steps like urnn_ed_sequence_dev (same workspace), every launch bracketed by
  * CUDA events on `stream`; synchronises once per step.  op_ms[i] = mean milliseconds of launch i, names = max_ops records of

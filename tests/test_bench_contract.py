@@ -1,5 +1,6 @@
-"""bench.py contract pieces that run without a GPU: the reference arm (CPU port of the reference's step, oracle/) prints
-one JSON line with the keys the driver reads; ranks other than 0 print nothing and exit 0."""
+"""bench.py contract pieces that run without a GPU: the reference arm (the unmodified reference modules from oracle/_ref,
+or the op-for-op torch port where that copy is absent) prints one JSON line with the keys the driver reads; ranks other
+than 0 print nothing and exit 0; both arms name the workload identically."""
 import json
 import os
 import subprocess
@@ -22,9 +23,13 @@ def test_reference_arm_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "cells*steps/s"
     assert d["metric"].startswith("grid-cells*steps/s")
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "src", "lib", "model", "networks", "model.py"))
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"]["workload"] == bench.workload_name(32, 32, 9)       # the string our arm emits for the same grid
 
 
 def test_reference_arm_other_ranks_are_silent():

@@ -312,6 +312,34 @@ static int ed_step_impl(const urnn_ed_desc* d, const urnn_ed_params* p, const St
 
 // ------------------------------------------------------------------------------------------------ host-buffer sequence
 // test.py:356-375 with host buffers: H2D of step t+1's input and D2H of step t-1's depth map overlap step t.
+// Copy streams / events of the host-buffer entry points: one set per device, created on first use on that device
+// (these entry points are the only ones that own CUDA objects).
+struct HostIo { cudaStream_t s_in = nullptr, s_out = nullptr; cudaEvent_t ev_in[2], ev_step[2], ev_out[2], ev_free[2], ev_start; };
+static std::mutex g_io_mu;
+static HostIo g_io[64];
+static bool g_io_ready[64] = {false};
+static int host_io(HostIo** out) {
+    int dev = 0;
+    URNN_CUDA(cudaGetDevice(&dev));
+    URNN_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_io_mu);
+    HostIo& io = g_io[dev];
+    if (!g_io_ready[dev]) {
+        URNN_CUDA(cudaStreamCreateWithFlags(&io.s_in, cudaStreamNonBlocking));
+        URNN_CUDA(cudaStreamCreateWithFlags(&io.s_out, cudaStreamNonBlocking));
+        URNN_CUDA(cudaEventCreateWithFlags(&io.ev_start, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            URNN_CUDA(cudaEventCreateWithFlags(&io.ev_in[i], cudaEventDisableTiming));
+            URNN_CUDA(cudaEventCreateWithFlags(&io.ev_step[i], cudaEventDisableTiming));
+            URNN_CUDA(cudaEventCreateWithFlags(&io.ev_out[i], cudaEventDisableTiming));
+            URNN_CUDA(cudaEventCreateWithFlags(&io.ev_free[i], cudaEventDisableTiming));
+        }
+        g_io_ready[dev] = true;
+    }
+    *out = &io;
+    return URNN_OK;
+}
+
 // frees a sequence context on every exit path
 struct SeqGuard { V2Seq* seq = nullptr; ~SeqGuard() { if (seq) v2_seq_end(seq, 0, nullptr, nullptr); } };
 
@@ -360,19 +388,10 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
     URNN_TRY(seq_plan(d, ws, ws_bytes, &sp));
     if (sp.total > ws_bytes) { set_error("ed_sequence_host: workspace %zu < %zu bytes", ws_bytes, sp.total); return URNN_E_WORKSPACE; }
     for (int k = 0; k < 6; ++k) { URNN_CHECK_ARG(states[k], "ed_sequence_host: null state %d", k); sp.st[0][k] = states[k]; }
-    // copy streams / events are created once per process (this entry point is the only one that owns CUDA objects)
-    static cudaStream_t s_in = nullptr, s_out = nullptr;
-    static cudaEvent_t ev_in[2], ev_step[2], ev_out[2], ev_free[2];
-    if (s_in == nullptr) {
-        URNN_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-        URNN_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            URNN_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-            URNN_CUDA(cudaEventCreateWithFlags(&ev_step[i], cudaEventDisableTiming));
-            URNN_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-            URNN_CUDA(cudaEventCreateWithFlags(&ev_free[i], cudaEventDisableTiming));
-        }
-    }
+    HostIo* io = nullptr;
+    URNN_TRY(host_io(&io));
+    cudaStream_t s_in = io->s_in, s_out = io->s_out;
+    cudaEvent_t *ev_in = io->ev_in, *ev_step = io->ev_step, *ev_out = io->ev_out, *ev_free = io->ev_free;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t N = (size_t)d->H * d->W, in_elems = (size_t)d->Cin * N;
     // the copy streams must not run ahead of work already queued on the caller's stream
@@ -417,6 +436,17 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
     URNN_CUDA(cudaStreamSynchronize(s_out));
     URNN_CUDA(cudaStreamSynchronize(st));
     return URNN_OK;
+}
+
+int64_t urnn_layout_index(int32_t H, int32_t W, int32_t level, int32_t y, int32_t x, int64_t* plane_elems) {
+#ifndef URNN_NO_TC
+    long long n = 0;
+    const long long r = v2_layout_index(H, W, level, y, x, &n);
+    if (plane_elems) *plane_elems = (int64_t)n;
+    return (int64_t)r;
+#else
+    (void)H; (void)W; (void)level; (void)y; (void)x; (void)plane_elems; return -1;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ device-buffer sequence
@@ -552,16 +582,10 @@ int urnn_ed_event_host(const urnn_ed_desc* d, const urnn_ed_params* p, const urn
     EventPlan ep;
     URNN_TRY(event_plan(d, ev, ws, ws_bytes, &ep));
     if (ep.total > ws_bytes) { set_error("ed_event: workspace %zu < %zu bytes", ws_bytes, ep.total); return URNN_E_WORKSPACE; }
-    static cudaStream_t s_out = nullptr;
-    static cudaEvent_t ev_step[2], ev_out[2], ev_start;
-    if (s_out == nullptr) {
-        URNN_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        URNN_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-        for (int i = 0; i < 2; ++i) {
-            URNN_CUDA(cudaEventCreateWithFlags(&ev_step[i], cudaEventDisableTiming));
-            URNN_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-        }
-    }
+    HostIo* io = nullptr;
+    URNN_TRY(host_io(&io));
+    cudaStream_t s_out = io->s_out;
+    cudaEvent_t *ev_step = io->ev_step, *ev_out = io->ev_out, ev_start = io->ev_start;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t N = (size_t)d->H * d->W;
     const int T = ev->T, cout0 = d->enc_conv[0];

@@ -14,7 +14,7 @@
 
 namespace urnn {
 
-static int g_num_sms = 0;
+// (no cached device properties: a process may drive several devices; the attribute query is a cached driver lookup)
 // Sweep direction: consecutive kernels walk the grid in opposite directions so that a kernel starts on the data its
 // predecessor touched last (still in the 126 MB L2).  Entry points reset it, so a given call sequence is reproducible.
 static thread_local int g_dir = 0;
@@ -28,11 +28,8 @@ long tc_pad_plane(long n) { return pad_plane(n); }
 
 template <bool GATED, int EPI, bool BULK>
 static int tc_launch_tb(tc::GemmParams& P, int grid, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<GATED, EPI, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
-        attr_set = true;
-    }
+    // per launch: the attribute is per device, and a process may use several (cheap driver call)
+    URNN_CUDA(cudaFuncSetAttribute(tc::gemm_gn_kernel<GATED, EPI, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_CAP));
     // Programmatic dependent launch: the next kernel's CTAs may start their prologue (barrier init, TMEM allocation,
     // weight conversion) while the previous kernel drains; they touch its outputs only after griddepcontrol.wait.
     static const bool pdl = !(getenv("URNN_PDL") && getenv("URNN_PDL")[0] == '0');
@@ -94,7 +91,8 @@ int tc_launch(tc::GemmParams& P, int epi, cudaStream_t st) {
         }
         ++g_wimg.idx;
     }
-    if (g_num_sms == 0) {
+    int g_num_sms = 0;
+    {
         int dev = 0;
         URNN_CUDA(cudaGetDevice(&dev));
         URNN_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));

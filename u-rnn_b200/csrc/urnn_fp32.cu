@@ -105,6 +105,7 @@ int cgru_fwd_fp32_passes(const urnn_cell_desc* d, const urnn_cell_params* p, con
     GnStatsEpilogue ep1;
     ep1.bias = p->b1; ep1.out = w.G; ep1.plane = N; ep1.vec = (N % 4 == 0);
     CommDev comm; current_comm(&comm);
+    if (comm.world > 1 && 2 * F / 32 > COMM_MAX_SETS) { set_error("cgru_fwd: num_features=%d > 128 cannot be sharded (%d GroupNorm groups per statistics exchange)", F, COMM_MAX_SETS); return URNN_E_UNSUPPORTED; }
     const double gcount = 32.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);
     ep1.sink = StatSink{w.partial1, w.total1, w.counter, 2 * F / 32, w.gx, comm};
     ep1.aff = AffineOut{w.scale1, w.shift1, p->gn1_w, p->gn1_b, 2 * F, 32, gcount, d->eps};

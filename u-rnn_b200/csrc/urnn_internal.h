@@ -48,6 +48,7 @@ int deconv2x2_lrelu_fwd_tc(int Cin, int Cout, int H, int W, float slope, const v
 // URNN_MATH_F16X3 (urnn_v2.cu): the step on the second-generation pixel GEMM; states stay in the internal split layout
 // between the steps of a sequence
 struct V2Seq;
+long long v2_layout_index(int H, int W, int level, int y, int x, long long* ntot);
 size_t v2_step_workspace_bytes(const urnn_ed_desc* d);
 int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float* x, int cin, const float* w, long long w_ld, const float* b,
                      const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);

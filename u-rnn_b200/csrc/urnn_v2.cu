@@ -629,6 +629,15 @@ int step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float* x
 
 }  // namespace v2
 
+// host-side view of the internal layout (tests, tools): position of pixel (y, x) of the level-`level` map; -1 if out of range
+long long v2_layout_index(int H, int W, int level, int y, int x, long long* ntot) {
+    if (H <= 0 || W <= 0 || H % 4 || W % 4 || level < 0 || level > 2) return -1;
+    const v2::Layout l = v2::make_layout(H, W, true);
+    if (ntot) *ntot = l.ntot[level];
+    if (y < 0 || x < 0 || y >= (H >> level) || x >= (W >> level)) return -1;
+    return v2::ix_internal(1, level, y, x, W >> level, W / 4, l.n4p);
+}
+
 // ---- entry points used by capi.cu
 size_t v2_step_workspace_bytes(const urnn_ed_desc* d) { return v2::step_workspace_bytes(d); }
 int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float* x, int cin, const float* w, long long w_ld, const float* b,

@@ -31,7 +31,7 @@ class CGRU_cell(nn.Module):
     module="encoder": hidden_state is h (B,F,H,W).  module="decoder": hidden_state is cat(e, d) (B,2F,H,W),
     only d is updated.  `use_checkpoint` is accepted for signature parity: the CUDA backward always
     recomputes the forward intermediates, which is what reentrant checkpointing does in the reference.
-    `math` (additive, optional): "fp32" | "tf32" | "bf16"; None follows urnn_b200.set_default_math().
+    `math` (additive, optional): "fp32" | "f16x3" | "bf16"; None follows urnn_b200.set_default_math().
     """
 
     def __init__(self, use_checkpoint, shape, input_channels, filter_size, num_features, module, math=None):
@@ -42,6 +42,8 @@ class CGRU_cell(nn.Module):
             # F < 32 fails in the reference too (GroupNorm(F//32 = 0 groups)); other non-multiples would need
             # GroupNorm groups wider than 32 channels, which the fused kernels do not implement
             raise ValueError(f"CGRU_cell: num_features={num_features} must be a multiple of 32")
+        if math is not None and math not in ("fp32", "f16x3", "bf16"):
+            raise ValueError(f"CGRU_cell: unknown math mode {math!r} (fp32 | f16x3 | bf16)")
         self.shape = shape
         self.input_channels = int(input_channels)
         self.filter_size = filter_size

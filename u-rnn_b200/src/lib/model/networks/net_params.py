@@ -18,7 +18,7 @@ DEFAULT_NET_CFG = {   # configs/network.yaml of the reference (published archite
 def get_network_params(use_checkpoint, input_height=500, input_width=500, input_channels=63, net_cfg=None,
                        math=None):
     """Returns ([encoder stem specs, encoder cells], [decoder stem specs, decoder cells]).
-    `math` is an additive option forwarded to every cell ("fp32" | "tf32" | "bf16" | None)."""
+    `math` is an additive option forwarded to every cell ("fp32" | "f16x3" | "bf16" | None)."""
     cfg = net_cfg if net_cfg is not None else DEFAULT_NET_CFG
     enc, dec = cfg["encoder"], cfg["decoder"]
     e_conv, e_gru, down, e_k = enc["conv_out_channels"], enc["gru_channels"], enc["downsample_factors"], enc["filter_size"]

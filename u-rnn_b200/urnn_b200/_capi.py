@@ -88,6 +88,7 @@ SIGNATURES = {
     "urnn_ed_sequence_dev_workspace_bytes": (sz, [C.POINTER(EdDesc)]),
     "urnn_ed_sequence_dev": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), i32, vp, vp, vp, C.POINTER(fp),
                                        vp, sz, vp]),
+    "urnn_layout_index": (C.c_int64, [i32, i32, i32, i32, i32, C.POINTER(C.c_int64)]),
     "urnn_ed_profile_dev": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), i32, vp, C.POINTER(fp), vp, sz, vp,
                                       vp, vp, i32, vp]),
     "urnn_ed_sequence_host_workspace_bytes": (sz, [C.POINTER(EdDesc)]),

@@ -20,7 +20,8 @@ _default_math = "fp32"
 
 
 def set_default_math(name):
-    """'fp32' (parity mode) or 'bf16' (tcgen05 mode) for modules that do not pin one."""
+    """'fp32' (FFMA parity mode), 'f16x3' (tcgen05, fp16 hi+lo split operands: the fast mode) or 'bf16' (tcgen05,
+    single-pass bf16: short horizons only) for modules that do not pin one."""
     global _default_math
     if name not in _capi.MATH_BY_NAME:
         raise ValueError(f"unknown math mode {name!r}")
@@ -45,6 +46,15 @@ def _chk(t, name, shape=None):
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
     return t if t.is_contiguous() else t.contiguous()
+
+
+def _empty_like_c(t):
+    """A CONTIGUOUS tensor of t's shape (empty_like preserves dense non-contiguous strides, the library expects NCHW)."""
+    return torch.empty(t.shape, dtype=t.dtype, device=t.device)
+
+
+def _c(t):
+    return None if t is None else (t if t.is_contiguous() else t.contiguous())
 
 
 def _p(t):
@@ -94,9 +104,9 @@ def cgru_cell_bwd(x, e, h, dh_out, params, grads, ksize, variant, need, math=Non
     Cx = params[0].shape[1] - Ch
     desc = CellDesc(H, W, Cx, F, ksize, variant, _math_code(math), eps)
     dh_out = _chk(dh_out, "dh_out", (F, H, W))
-    dx = torch.empty_like(x) if (x is not None and need[0]) else None
-    de = torch.empty_like(e) if (e is not None and need[1]) else None
-    dh = torch.empty_like(h) if need[2] else None
+    dx = _empty_like_c(x) if (x is not None and need[0]) else None
+    de = _empty_like_c(e) if (e is not None and need[1]) else None
+    dh = _empty_like_c(h) if need[2] else None
     ws = _ws(lib.urnn_cgru_bwd_workspace_bytes(C.byref(desc)), h.device)
     cp = cell_params_struct(*params)
     cg = CellGrads(*[_p(t) for t in grads])
@@ -112,6 +122,8 @@ class CgruCellFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, e, h, ksize, variant, math, *params):
         ctx.cfg = (ksize, variant, math)
+        x, e, h = _c(x), _c(e), _c(h)            # the backward hands raw pointers of the saved tensors to the library
+        params = tuple(_c(p) for p in params)
         ctx.save_for_backward(*[t for t in (x, e, h) if t is not None], *params)
         ctx.has = (x is not None, e is not None)
         with torch.no_grad():
@@ -154,6 +166,7 @@ def conv1x1_lrelu_fwd(x, w, b, pool=1, slope=LRELU_SLOPE, math=None):
 class Conv1x1LreluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, pool, slope, math):
+        x, w, b = _c(x), _c(w), _c(b)
         ctx.cfg = (pool, slope)
         ctx.save_for_backward(x, w, b)
         with torch.no_grad():
@@ -167,7 +180,7 @@ class Conv1x1LreluFn(torch.autograd.Function):
         Cin, H, W = x.shape
         Cout = w.shape[0]
         dy = _chk(dy, "dy", (Cout, H // pool, W // pool))
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dx = _empty_like_c(x) if ctx.needs_input_grad[0] else None
         dw, db = torch.zeros_like(w), torch.zeros_like(b)
         ws = _ws(lib.urnn_conv1x1_lrelu_bwd_workspace_bytes(Cin, Cout, H, W, pool), x.device)
         _capi.check(lib.urnn_conv1x1_lrelu_bwd(Cin, Cout, H, W, pool, slope, _p(x), _p(w), _p(b), _p(dy), _p(dx),
@@ -197,6 +210,7 @@ def deconv2x2_lrelu_fwd(x, w, b, slope=LRELU_SLOPE, math=None):
 class Deconv2x2LreluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, slope, math):
+        x, w, b = _c(x), _c(w), _c(b)
         ctx.slope = slope
         ctx.save_for_backward(x, w, b)
         with torch.no_grad():
@@ -209,7 +223,7 @@ class Deconv2x2LreluFn(torch.autograd.Function):
         Cin, H, W = x.shape
         Cout = w.shape[1]
         dy = _chk(dy, "dy", (Cout, 2 * H, 2 * W))
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dx = _empty_like_c(x) if ctx.needs_input_grad[0] else None
         dw, db = torch.zeros_like(w), torch.zeros_like(b)
         ws = _ws(lib.urnn_deconv2x2_lrelu_bwd_workspace_bytes(Cin, Cout, H, W), x.device)
         _capi.check(lib.urnn_deconv2x2_lrelu_bwd(Cin, Cout, H, W, ctx.slope, _p(x), _p(w), _p(b), _p(dy), _p(dx),
@@ -255,9 +269,10 @@ def head_fwd(feat, p, cls_thred, ln_eps=LN_EPS, slope=LRELU_SLOPE):
     C16, H, W = feat.shape
     if C16 != 16:
         raise ValueError(f"head: expected 16 feature channels, got {C16}")
-    for i in range(5):
-        _chk(p["conv_w"][i], "head conv weight", (16, 16, 1, 1))
-        _chk(p["ln_w"][i], "head ln weight", (16, H, W)); _chk(p["ln_b"][i], "head ln bias", (16, H, W))
+    p = dict(p)                                  # the checked (contiguous) tensors are the ones whose pointers are passed
+    p["conv_w"] = [_chk(t, "head conv weight", (16, 16, 1, 1)) for t in p["conv_w"]]
+    p["ln_w"] = [_chk(t, "head ln weight", (16, H, W)) for t in p["ln_w"]]
+    p["ln_b"] = [_chk(t, "head ln bias", (16, H, W)) for t in p["ln_b"]]
     out = torch.empty((2, H, W), dtype=torch.float32, device=feat.device)
     ws = _ws(lib.urnn_head_fwd_workspace_bytes(H, W), feat.device)
     hp = head_params_struct(p)
@@ -269,6 +284,8 @@ def head_fwd(feat, p, cls_thred, ln_eps=LN_EPS, slope=LRELU_SLOPE):
 class HeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, cls_thred, *flat):
+        feat = _c(feat)
+        flat = tuple(_c(t) for t in flat)
         ctx.cls_thred = cls_thred
         ctx.save_for_backward(feat, *flat)
         with torch.no_grad():
@@ -280,7 +297,7 @@ class HeadFn(torch.autograd.Function):
         feat, *flat = ctx.saved_tensors
         _, H, W = feat.shape
         dout = _chk(dout, "dout", (2, H, W))
-        dfeat = torch.empty_like(feat)
+        dfeat = _empty_like_c(feat)
         gflat = [torch.zeros_like(t) for t in flat]
         hp = head_params_struct(_head_dict(flat))
         hg = HeadGrads()
