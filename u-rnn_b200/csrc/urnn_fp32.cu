@@ -3,7 +3,6 @@
 #include "pixgemm.cuh"
 #include <stdlib.h>
 #include "head.cuh"
-#include "head2.cuh"
 #include "urnn_internal.h"
 
 namespace urnn {
@@ -219,30 +218,6 @@ int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, cons
     head_kernel<1><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
     head_kernel<2><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
     head_kernel<3><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();
-    return URNN_OK;
-}
-
-// streaming kernels (head2.cuh): same workspace, same statistics plumbing; used by the f16x3 step
-int head_fwd_stream(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
-                    const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    HeadWs w;
-    size_t need = head_ws_layout(H, W, ws, ws_bytes, &w);
-    if (need > ws_bytes) { set_error("head_fwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
-    const long N = (long)H * W;
-    if (N % 2 || ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 7)) return head_fwd_fp32(H, W, cls_thred, ln_eps, slope, p, feat, out, ws, ws_bytes, st);
-    for (int i = 0; i < 5; ++i)
-        if ((reinterpret_cast<uintptr_t>(p->ln_w[i]) | reinterpret_cast<uintptr_t>(p->ln_b[i])) & 7) return head_fwd_fp32(H, W, cls_thred, ln_eps, slope, p, feat, out, ws, ws_bytes, st);
-    URNN_CUDA(cudaMemsetAsync(w.counter, 0, 64 * sizeof(unsigned), st));
-    HeadDev hd;
-    hd.p = *p; hd.cls_thred = cls_thred; hd.eps = ln_eps; hd.slope = slope; hd.plane = N;
-    CommDev comm; current_comm(&comm);
-    hd.count = 16.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);
-    hd.sink = StatSink{w.partial, w.total, w.counter, 5, w.gx, comm};
-    const unsigned gx = (unsigned)((N / head2::PX + head2::TPB - 1) / head2::TPB);
-    head2::stem_stats_kernel<<<gx, head2::TPB, 0, st>>>(hd, feat, N); URNN_LAUNCH_CHECK();
-    head2::stage1_kernel<<<dim3(gx, 2), head2::TPB, 0, st>>>(hd, feat, w.bufA, w.bufB, N); URNN_LAUNCH_CHECK();
-    head2::stage2_kernel<<<dim3(gx, 2), head2::TPB, 0, st>>>(hd, w.bufA, w.bufB, N); URNN_LAUNCH_CHECK();
-    head2::stage3_kernel<<<gx, head2::TPB, 0, st>>>(hd, w.bufA, w.bufB, out, N); URNN_LAUNCH_CHECK();
     return URNN_OK;
 }
 

@@ -72,9 +72,6 @@ size_t head_fwd_fp32_workspace(int H, int W);
 int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
                   const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 
-int head_fwd_stream(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
-                    const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
-
 // backward, fp32 (urnn_bwd.cu)
 size_t conv1x1_lrelu_bwd_workspace(int Cin, int Cout, int H, int W, int pool);
 int conv1x1_lrelu_bwd_fp32(int Cin, int Cout, int H, int W, int pool, float slope, const float* x, const float* w,

@@ -555,7 +555,7 @@ int step(Plan& pl, int parity, const float* x, int cin, const float* w, long lon
         V2_EV();
     }
     V2_EV();
-    URNN_TRY(head_fwd_stream(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, st));
+    URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, st));
     V2_EV();
 #undef V2_EV
     return URNN_OK;
