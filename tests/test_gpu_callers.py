@@ -25,6 +25,13 @@ def ref_callers():
         pytest.skip("oracle/_ref is not built (python oracle/make_ref.py in the build container)")
     if REF not in sys.path:
         sys.path.append(REF)                    # after the drop-in package: the overlay of INTEGRATION.md
+    # earlier tests may have imported the drop-in packages before the overlay path existed: recompute their search paths
+    # (what their __init__ does at first import, pkgutil.extend_path)
+    import pkgutil
+    import src.lib.model as pkg_model
+    import src.lib.model.networks as pkg_networks
+    for pkg in (pkg_model, pkg_networks):
+        pkg.__path__ = pkgutil.extend_path(pkg.__path__, pkg.__name__)
     import callers
     import src.lib.model.networks.model as m
     assert "u-rnn_b200" in m.__file__           # the network under the reference's loops is ours

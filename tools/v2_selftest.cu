@@ -123,7 +123,7 @@ static int run_case(const Case& cs, int num_sms) {
         P.out_hi = d_split; P.out_lo = (long long)outC * out_ntot; P.out_plane = out_ntot; P.out_acc_stride = cs.ntot;
     } else {
         CK(cudaMalloc(&d_out, (size_t)outC * out_ntot * 4)); CK(cudaMemset(d_out, 0, (size_t)outC * out_ntot * 4));
-        P.out_f32 = d_out; P.out_plane = out_ntot; P.store_c0 = 0; P.store_c1 = cs.N;
+        P.out_f32 = d_out; P.out_plane = out_ntot; P.store_c0 = 0; P.store_c1 = getenv("V2_NOSTORE") ? 0 : cs.N;
     }
     // statistics
     float4* d_part = nullptr; double* d_tot = nullptr; unsigned* d_cnt = nullptr; float *d_scale = nullptr, *d_shift = nullptr, *d_gamma = nullptr, *d_beta = nullptr;
@@ -164,6 +164,8 @@ static int run_case(const Case& cs, int num_sms) {
             for (int b = 0; b < L.grid; b += 7) printf(" [%d: %.1f %.1f sm%lld]", b, (h[9 * 32 + b] - tmin) * 1e-3, (h[9 * 32 + 256 + b] - tmin) * 1e-3, h[9 * 32 + 512 + b]);
             double emax = 0, emin = 1e30; for (int b = 0; b < L.grid; ++b) { double e = (h[9 * 32 + 256 + b] - tmin) * 1e-3; if (e > emax) emax = e; if (e < emin) emin = e; }
             printf("\n   CTA end times: min %.1f us max %.1f us\n", emin, emax);
+            printf("   first CTA entry %.1f us | last CTA past its partials %.1f us | last CTA exit (after finalize) %.1f us\n",
+                   ((long long)~(unsigned long long)h[8 * 32 + 1] - tmin) * 1e-3, (h[8 * 32 + 2] - tmin) * 1e-3, (h[8 * 32 + 3] - tmin) * 1e-3);
         }
         const long long t0 = h[8 * 32];
         printf("   timeline of CTA 0 (cycles since setup done): tile: tma_first tma_last | mma_tempty mma_full0 mma_fullN mma_commit | epi_wake epi_done\n");

@@ -90,6 +90,12 @@ __device__ __forceinline__ void stats2_exchange(const StatSink2& s) {
 // Called by ALL threads of the CTA after its partials are written.  The last CTA merges, exchanges, folds the affine.
 __device__ __forceinline__ void stats2_finalize_last_cta(const StatSink2& s, int ncontrib, unsigned ncta_total, const AffineOut* aff) {
     __shared__ bool is_last;
+    __shared__ double tot_s[MAXG * 4];
+    // the affine parameters of "my" channel are fetched by every CTA before the fence (a wasted 8-byte load for all but the
+    // last one): the finalizer is a serial tail of the launch, every dependent round trip to L2 in it costs ~1 us
+    const bool want_aff = aff != nullptr && aff->scale != nullptr;
+    float gamma_c = 0.f, beta_c = 0.f;
+    if (want_aff && (int)threadIdx.x < aff->channels) { gamma_c = __ldg(aff->gamma + threadIdx.x); beta_c = __ldg(aff->beta + threadIdx.x); }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -99,16 +105,23 @@ __device__ __forceinline__ void stats2_finalize_last_cta(const StatSink2& s, int
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // one warp per set; the partials (one per CTA) are re-referenced to the first partial's pilot K00 in double -- only
-    // multiplies and adds, no divisions in the loop (a single warp runs ~8 cycles per dependent instruction) -- and summed
-    // in a fixed order: lane-strided, then a fixed shuffle tree.
+    // one warp per set; the partials (one per CTA) are re-referenced to the first non-empty partial's pilot K00 in double --
+    // only multiplies and adds, no divisions in the loop (a single warp runs ~8 cycles per dependent instruction) -- and
+    // summed in a fixed order: lane-strided, then a fixed shuffle tree.
     const int nwarp = blockDim.x >> 5, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int set = warp; set < s.nsets; set += nwarp) {
+        const float4* part = s.partial + (size_t)set * s.stride;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < ncontrib) v0 = __ldcg(part + lane);
         double k00 = 0.0;
-        for (int i = 0; i < ncontrib; ++i) { const float4 v = __ldcg(&s.partial[(size_t)set * s.stride + i]); if (v.x > 0.f) { k00 = (double)v.w; break; } }
+        {
+            const unsigned have = __ballot_sync(0xffffffffu, v0.x > 0.f);
+            if (have) k00 = (double)__shfl_sync(0xffffffffu, v0.w, __ffs(have) - 1);
+            else for (int i = 32; i < ncontrib; ++i) { const float4 v = __ldcg(part + i); if (v.x > 0.f) { k00 = (double)v.w; break; } }
+        }
         double n = 0.0, a1 = 0.0, a2 = 0.0;
         for (int i = lane; i < ncontrib; i += 32) {
-            const float4 v = __ldcg(&s.partial[(size_t)set * s.stride + i]);
+            const float4 v = i == lane ? v0 : __ldcg(part + i);
             if (!(v.x > 0.f)) continue;              // empty partial (all-padding CTA): its pilot may be garbage
             const double nb = (double)v.x, s1 = (double)v.y, s2 = (double)v.z, d = (double)v.w - k00;
             n += nb; a1 += s1 + nb * d; a2 += s2 + 2.0 * d * s1 + nb * d * d;
@@ -119,21 +132,26 @@ __device__ __forceinline__ void stats2_finalize_last_cta(const StatSink2& s, int
             double m2 = a2 - a1 * m;                 // sum (x - mean)^2
             if (m2 < 0.0) m2 = 0.0;
             s.total[4 * set] = k00 + m; s.total[4 * set + 1] = m2; s.total[4 * set + 2] = n;
+            tot_s[4 * set] = k00 + m; tot_s[4 * set + 1] = m2; tot_s[4 * set + 2] = n;
         }
     }
     __syncthreads();
-    stats2_exchange(s);
-    if (aff != nullptr && aff->scale != nullptr) {
-        __threadfence();
+    if (s.comm.world > 1) {
+        stats2_exchange(s);
+        if ((int)threadIdx.x < 4 * s.nsets) tot_s[threadIdx.x] = s.total[threadIdx.x];
+        __syncthreads();
+    }
+    if (want_aff) {
         for (int c = threadIdx.x; c < aff->channels; c += blockDim.x) {
             const int set = c / aff->ch_per_set;
-            const double mean = s.total[4 * set], n = s.total[4 * set + 2];
-            double var = n > 0.0 ? s.total[4 * set + 1] / n : 0.0;
+            const double mean = tot_s[4 * set], n = tot_s[4 * set + 2];
+            double var = n > 0.0 ? tot_s[4 * set + 1] / n : 0.0;
             if (var < 0.0) var = 0.0;
             const double rstd = 1.0 / sqrt(var + (double)aff->eps);
-            const double sc = (double)aff->gamma[c] * rstd;
+            const bool mine = c == (int)threadIdx.x;
+            const double sc = (double)(mine ? gamma_c : aff->gamma[c]) * rstd;
             aff->scale[c] = (float)sc;
-            aff->shift[c] = (float)((double)aff->beta[c] - mean * sc);
+            aff->shift[c] = (float)((double)(mine ? beta_c : aff->beta[c]) - mean * sc);
         }
     }
     if (threadIdx.x == 0) *s.counter = 0u;
@@ -150,8 +168,21 @@ struct Step {                 // one TMA-loaded operand unit of a tile
     long long pix_off;        // added to the tile's first pixel (phase block offsets)
 };
 
+// What the MMA issuer needs per operand unit, precomputed by plan_gemm (descriptors relative to the CTA's shared-memory
+// base: the start-address field is additive, the kernel adds base >> 4 and the ring slot).
+struct MmaStep {
+    unsigned long long a_desc;        // hi half of the unit in ring slot 0
+    unsigned long long b_desc[2];     // weight rows (hi image) of the unit's first / second K = 16 group
+    unsigned a_lo_delta;              // descriptor distance hi -> lo half of the unit
+    unsigned d_off;                   // accumulator column offset inside the stage
+    unsigned first;                   // 0: this unit's first MMA overwrites the accumulator
+    unsigned nj;                      // K = 16 groups in the unit (1 or 2)
+};
+constexpr int MAX_ACC_STAGES = 4;
+
 struct GemmParams {
     Step steps[MAX_STEPS]; int nsteps;
+    MmaStep msteps[MAX_STEPS];
     int nacc, acc_mode;
     // reset-gated operand segment (candidate GEMM): r*h with r = sigmoid(gate_pre*scale + shift), produced by the gate warps
     int gate_ch;                                   // 0: none, else F (multiple of 32)
@@ -219,22 +250,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
     constexpr int GATE_WARP0 = EPI_WARP0 + NWE;
     const int ncols_total = P.acc_mode == ACC_DECONV ? P.nacc * P.N : P.N;
     const SmemPlan L = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total);
-    // barriers: full[8] | empty[8] | tfull[2] | tempty[2] | gfull[2] | gempty[2] | tmem slot
-    const uint32_t full0 = base + L.bar_off, empty0 = full0 + 64, tfull0 = empty0 + 64, tempty0 = tfull0 + 16;
-    const uint32_t gfull0 = tempty0 + 16, gempty0 = gfull0 + 16;
+    // barriers: full[8] | empty[8] | tfull[4] | tempty[4] | gfull[2] | gempty[2] | tmem slot
+    const uint32_t full0 = base + L.bar_off, empty0 = full0 + 64, tfull0 = empty0 + 64, tempty0 = tfull0 + 32;
+    const uint32_t gfull0 = tempty0 + 32, gempty0 = gfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L.bar_off + 256);
     float* sbias = reinterpret_cast<float*>(sm + L.bias_off);
     float* sgaff = reinterpret_cast<float*>(sm + L.gaff_off);
     float4* red = reinterpret_cast<float4*>(sm + L.red_off);     // [NWARP_EPI][MAXG] = (n, S1, S2, K)
 
+    if (P.dbg && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax((unsigned long long*)&P.dbg[8 * 32 + 1], ~t_); }
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- one-time setup (reads only parameters and the constant weight image)
     if (tid == 0) {
         for (int s = 0; s < P.nslots; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NWE);
-            mbar_init(gfull0 + 8 * a, NWARP_GATE); mbar_init(gempty0 + 8 * a, 1);
-        }
+        for (int a = 0; a < MAX_ACC_STAGES; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, NWE); }
+        for (int a = 0; a < 2; ++a) { mbar_init(gfull0 + 8 * a, NWARP_GATE); mbar_init(gempty0 + 8 * a, 1); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&map0); tma_prefetch_desc(&map1); tma_prefetch_desc(&map2); }
@@ -307,8 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         // lane issues tcgen05.mma / tcgen05.commit.
         const uint32_t idesc = instr_desc_16(P.N, SPLIT_FMT);
         int slot = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0; int gd = 0; uint32_t gph = 0;
-        const uint32_t hl = P.nmma == 3 ? 2u : 1u;
-        const uint32_t wlo16 = wlo >> 4;
+        const uint32_t wlo16 = wlo >> 4, base16 = base >> 4;
         int ti = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
             mbar_wait(tempty0 + 8 * as, aph ^ 1);
@@ -316,32 +345,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
             V2_STAMP(2, ti);
             const uint32_t d0 = tmem_base + (uint32_t)(as * P.nacc * P.acc_stride);
             for (int s = 0; s < P.nsteps; ++s) {
-                const int unit_ch = P.steps[s].unit_ch, kg = P.steps[s].kglob, acc = P.steps[s].acc;
+                const MmaStep& m = P.msteps[s];
                 mbar_wait(full0 + 8 * slot, ph);
                 tc_fence_after();
                 if (s == 0) V2_STAMP(3, ti);
                 if (s == P.nsteps - 1) V2_STAMP(4, ti);
-                const uint32_t a_base = base + L.ring_off + (uint32_t)slot * SLOT_BYTES;
-                const uint64_t a0 = smem_desc_mn_sw128(a_base, (uint32_t)unit_ch * 128u * hl);
-                const uint32_t a_lo_delta = ((uint32_t)unit_ch * 128u) >> 4;
-                const uint64_t b0 = smem_desc_sw128(base + L.w_off + (uint32_t)(kg >> 6) * P.nrows * 128u + (uint32_t)((kg & 63) >> 4) * 32u);
-                const int kg1 = kg + 16;               // the second K=16 group may start the next 64-channel weight block
-                const uint64_t b1 = smem_desc_sw128(base + L.w_off + (uint32_t)(kg1 >> 6) * P.nrows * 128u + (uint32_t)((kg1 & 63) >> 4) * 32u);
-                const uint32_t first0 = (P.acc_mode == ACC_POOL ? kg : s) == 0 ? 0u : 1u;
+                const uint64_t a_hi = m.a_desc + (uint64_t)(base16 + (uint32_t)slot * (SLOT_BYTES >> 4));
+                const uint64_t a_lo = a_hi + m.a_lo_delta;
+                const uint64_t b0 = m.b_desc[0] + base16, b1 = m.b_desc[1] + base16;
+                const uint32_t d = d0 + m.d_off;
                 if (elect_one()) {
-                    for (int j = 0; j < (unit_ch >> 4); ++j) {
-                        const uint64_t a_hi = a0 + (uint32_t)(j * 128), a_lo = a_hi + a_lo_delta, b_hi = j == 0 ? b0 : b1;
-                        const uint32_t first = j == 0 ? first0 : 1u;
-                        if (P.acc_mode != ACC_DECONV) {
-                            const uint32_t d = d0 + (uint32_t)(acc * P.acc_stride);
-                            umma_f16(d, a_hi, b_hi, idesc, first);
-                            if (P.nmma == 3) { umma_f16(d, a_lo, b_hi, idesc, 1u); umma_f16(d, a_hi, b_hi + wlo16, idesc, 1u); }
-                        } else {
+                    if (P.acc_mode != ACC_DECONV) {
+                        umma_f16(d, a_hi, b0, idesc, m.first);
+                        umma_f16(d, a_lo, b0, idesc, 1u);
+                        umma_f16(d, a_hi, b0 + wlo16, idesc, 1u);
+                        if (m.nj == 2) {
+                            umma_f16(d, a_hi + 128, b1, idesc, 1u);
+                            umma_f16(d, a_lo + 128, b1, idesc, 1u);
+                            umma_f16(d, a_hi + 128, b1 + wlo16, idesc, 1u);
+                        }
+                    } else {
+                        for (uint32_t j = 0; j < m.nj; ++j) {
+                            const uint64_t bj = j == 0 ? b0 : b1;
                             for (int a = 0; a < P.nacc; ++a) {
-                                const uint32_t d = d0 + (uint32_t)(a * P.acc_stride);
-                                const uint64_t b = b_hi + (uint32_t)((a * P.N * 128) >> 4);
-                                umma_f16(d, a_hi, b, idesc, first);
-                                if (P.nmma == 3) { umma_f16(d, a_lo, b, idesc, 1u); umma_f16(d, a_hi, b + wlo16, idesc, 1u); }
+                                const uint32_t da = d + (uint32_t)(a * P.acc_stride);
+                                const uint64_t b = bj + (uint32_t)((a * P.N * 128) >> 4);
+                                umma_f16(da, a_hi + 128 * j, b, idesc, j == 0 ? m.first : 1u);
+                                umma_f16(da, a_lo + 128 * j, b, idesc, 1u);
+                                umma_f16(da, a_hi + 128 * j, b + wlo16, idesc, 1u);
                             }
                         }
                     }
@@ -363,7 +394,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
                             const uint64_t a_hi = smem_desc_mn_sw128(a, 8192), a_lo = a_hi + (4096 >> 4);
                             const uint32_t first = (P.nsteps == 0 && (u | j) == 0) ? 0u : 1u;
                             umma_f16(d0, a_hi, b, idesc, first);
-                            if (P.nmma == 3) { umma_f16(d0, a_lo, b, idesc, 1u); umma_f16(d0, a_hi, b + wlo16, idesc, 1u); }
+                            umma_f16(d0, a_lo, b, idesc, 1u); umma_f16(d0, a_hi, b + wlo16, idesc, 1u);
                         }
                     umma_commit(gempty0 + 8 * gd);
                 }
@@ -568,7 +599,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
         P.sink.partial[(size_t)g * P.sink.stride + blockIdx.x] = have ? make_float4((float)n, (float)a1, (float)a2, k0) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols); }
+    if (P.dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax((unsigned long long*)&P.dbg[8 * 32 + 2], t_); }
     if (P.epi == EPI_STATS_F32 && P.nstat > 0) stats2_finalize_last_cta(P.sink, gridDim.x, gridDim.x, &P.aff);
+    if (P.dbg && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); atomicMax((unsigned long long*)&P.dbg[8 * 32 + 3], t_); }
 }
 
 // ---- weight images: hi and lo bf16 parts of W^T, K-major rows of 128 bytes (64 channels), SWIZZLE_128B

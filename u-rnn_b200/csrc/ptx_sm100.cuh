@@ -100,7 +100,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart): weights
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+__host__ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address
     d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
@@ -111,7 +111,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 }
 // MN-major (pixel-contiguous) A tile, 128-byte swizzle: 1024-byte atoms of 8 K-rows x 64 MN elements;
 // leading byte offset = distance between atoms along MN, stride byte offset = along K (1024).
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo) {
+__host__ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)(lbo >> 4) << 16;

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(64) stem1_kernel(const Stem1Args a) {
 }
 
 // ------------------------------------------------------------------------------------------------ plan
-struct Op { int kind; GemmLaunch g; BlendArgs b; char name[24]; };     // kind 0: GEMM, 1: blend
+struct Op { int kind; GemmLaunch g; BlendArgs b; ChainLaunch c; char name[24]; };     // kind 0: GEMM, 1: blend, 2: chain (recompute) sweep
+static inline const void*& op_wimg(Op& o) { return o.kind == 2 ? o.c.P.wimg : o.g.P.wimg; }
 struct StatBufs { float4* partial; double* total; unsigned* counter; };
 
 struct Plan {
@@ -269,6 +270,10 @@ static void fill_common(GemmParams& P, const Plan& pl, int level) {
     P.ntot = pl.lay.ntot[level]; P.blk_stride = pl.lay.blk_stride; P.blk_valid = pl.lay.blk_valid; P.nmma = 3; P.slope = pl.d.lrelu_slope;
 }
 
+static int build_cell_y(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
+                        const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity);
+static bool chain_fits(int F, int Keff);
+
 // One (Skip-)ConvGRU cell step (ConvRNN.py:140-190) as sweep A (gates, GN-1 statistics), sweep B (candidate, GN-2
 // statistics) and the blend.  x / e may be absent (decoder stage 3: x = None -> its weight columns are skipped; encoder: no e).
 static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
@@ -278,6 +283,7 @@ static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_
     const int Ktot = Cx + Ch, kskip = x ? 0 : Cx, Keff = Ktot - kskip;
     const long long ntot = pl.lay.ntot[level];
     if (F % 32 || (x && x->C % 16) || Keff % 16) { set_error("cell(f16x3): channel counts must be multiples of 16 (Cx=%d F=%d)", Cx, F); return URNN_E_UNSUPPORTED; }
+    if (chain_fits(F, Keff)) return build_cell_y(pl, ops, sa, cd, cp, level, x, e, h, hout, first_parity);
     CommDev comm; current_comm(&comm);
     // ---- sweep A: G = W1 u + b1 (2F channels), in chunks of output channels whose hi+lo weight image fits beside the ring
     const int nkb = (Keff + 63) / 64;
@@ -336,6 +342,90 @@ static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_
     {
         Op op; op.kind = 1; memset(&op.g, 0, sizeof(op.g));
         op.b = BlendArgs{pl.G, pl.C, h.hi, h.lo_off(), hout.hi, hout.lo_off(), scale1, shift1, scale2, shift2, F, ntot};
+        ops.push_back(op);
+    }
+    return URNN_OK;
+}
+
+// The same cell as three recompute sweeps (gemm_v2_chain.cuh): the pre-norm maps G and C stay in tensor memory.
+//   A: G statistics (no store) -> GN-1 affine;  B': r*h from TMEM, C statistics -> GN-2 affine;  C': z, r, C again, blend, store h'.
+// Used when [W1 ; W2] hi + lo (3F rows) fit in shared memory next to the gate buffers and a ring of >= 3 slots.
+static bool chain_fits(int F, int Keff) {
+    // Opt-in (URNN_V2_Y=1).  Measured on B200 at 500 x 500, encoder stage 1: A 39 + B' 60 + C' 91 = 190 us against 163 us for
+    // the materialising schedule, although DRAM traffic drops from 672 MB to 276 MB: both chain sweeps are bound by SIMT issue
+    // (23 / 45 instructions per element in the gate / blend stages at 0.6 IPC per scheduler), not by HBM.
+    const char* e = getenv("URNN_V2_Y");
+    if (!e || atoi(e) == 0) return false;
+    if (F % 32 || 3 * F > 256) return false;
+    const int nkb = (Keff + 63) / 64;
+    return chain_slots(nkb, 3 * F, F, 2) >= 3 || chain_slots(nkb, 3 * F, F, 1) >= 3;
+}
+
+static int build_cell_y(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
+                        const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity) {
+    const int F = cd.F, Cx = cd.Cx;
+    const int Ch = cd.variant == URNN_CELL_DECODER ? 2 * F : F;
+    const int Ktot = Cx + Ch, kskip = x ? 0 : Cx, Keff = Ktot - kskip;
+    const long long ntot = pl.lay.ntot[level];
+    const int nkb = (Keff + 63) / 64;
+    CommDev comm; current_comm(&comm);
+    float *scale1 = nullptr, *shift1 = nullptr, *scale2 = nullptr, *shift2 = nullptr;
+    if (!take_affine(sa, 2 * F, &scale1, &shift1) || !take_affine(sa, F, &scale2, &shift2)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
+    // ---- sweep A: statistics of G = W1 u + b1
+    {
+        Op op; op.kind = 0; memset(&op.g, 0, sizeof(op.g)); params_defaults(op.g.P);
+        GemmParams& P = op.g.P; fill_common(P, pl, level);
+        int k = 0, m = 0;
+        const SplitMap* segs[3] = {nullptr, nullptr, nullptr};
+        if (x) { segs[m] = x; k = add_segment_steps(op.g, m, x->C, k, 0, 0); ++m; }
+        if (e) { segs[m] = e; k = add_segment_steps(op.g, m, e->C, k, 0, 0); ++m; }
+        segs[m] = &h; k = add_segment_steps(op.g, m, h.C, k, 0, 0); ++m;
+        for (int i = 0; i < 3; ++i) { const SplitMap* sm = segs[i] ? segs[i] : &h; URNN_TRY(make_split_tmap(&op.g.maps[i], *sm, sm->C % 32 == 0 ? 32 : 16, 2)); }
+        const int N = 2 * F;
+        P.N = N; P.nrows = N; P.nkb = nkb;
+        P.wimg = first_parity ? add_wimg(pl, cp.w1, Ktot, 1, 0, 1 << 30, N, N, Keff, kskip) : nullptr;
+        P.bias = cp.b1; P.nbias = N;
+        P.epi = EPI_STATS_F32; P.out_f32 = nullptr; P.out_plane = ntot; P.store_c0 = 0; P.store_c1 = 0;      // nothing stored
+        StatBufs sb;
+        if (!take_stats(sa, N / 32, pl.num_sms, &sb)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
+        P.nstat = N / 32;
+        P.sink.partial = sb.partial; P.sink.total = sb.total; P.sink.counter = sb.counter; P.sink.nsets = N / 32; P.sink.stride = pl.num_sms; P.sink.comm = comm;
+        P.aff.scale = scale1; P.aff.shift = shift1; P.aff.gamma = cp.gn1_w; P.aff.beta = cp.gn1_b; P.aff.channels = N; P.aff.ch_per_set = 32; P.aff.eps = cd.eps;
+        URNN_TRY(plan_gemm(op.g, pl.num_sms));
+        ops.push_back(op);
+    }
+    // ---- sweeps B' (final = 0: rows [W1_r ; W2]) and C' (final = 1: rows [W1_z ; W1_r ; W2])
+    for (int fin = 0; fin < 2; ++fin) {
+        Op op; op.kind = 2; memset(&op.g, 0, sizeof(op.g)); memset(&op.c, 0, sizeof(op.c));
+        ChainParams& P = op.c.P;
+        P.ntot = ntot; P.blk_stride = pl.lay.blk_stride; P.blk_valid = pl.lay.blk_valid;
+        P.F = F; P.final = fin;
+        P.N = fin ? 3 * F : 2 * F; P.nrows = P.N; P.nkb = nkb;
+        P.col_z = fin ? 0 : -1; P.col_r = fin ? F : 0; P.col_c = fin ? 2 * F : F;
+        int k = 0, m = 0;
+        const SplitMap* segs[3] = {nullptr, nullptr, nullptr};
+        if (x) { segs[m] = x; k = add_chain_steps(op.c, m, x->C, k, P.N); ++m; }
+        if (e) { segs[m] = e; k = add_chain_steps(op.c, m, e->C, k, P.N); ++m; }
+        P.gate_k0 = k;
+        segs[m] = &h; k = add_chain_steps(op.c, m, h.C, k, P.col_c); ++m;
+        if (k < 0) { set_error("cell(f16x3): too many operand units"); return URNN_E_UNSUPPORTED; }
+        for (int i = 0; i < 3; ++i) { const SplitMap* sm = segs[i] ? segs[i] : &h; URNN_TRY(make_split_tmap(&op.c.maps[i], *sm, sm->C % 32 == 0 ? 32 : 16, 2)); }
+        P.h = h.hi; P.h_plane = ntot; P.h_lo = h.lo_off();
+        // image rows: block 0 = the W1 rows of this sweep, block 1 = W2 (element offset between the two matrices; both are device fp32)
+        const float* w1rows = fin ? cp.w1 : cp.w1 + (long long)F * Ktot;
+        const int r1 = fin ? 2 * F : F;
+        P.wimg = first_parity ? add_wimg(pl, w1rows, Ktot, 1, (long long)(cp.w2 - w1rows), r1, P.N, P.N, Keff, kskip) : nullptr;
+        P.bias_z = fin ? cp.b1 : nullptr; P.bias_r = cp.b1 + F; P.bias_c = cp.b2;
+        P.scale_z = scale1; P.shift_z = shift1; P.scale_r = scale1 + F; P.shift_r = shift1 + F; P.scale_c = scale2; P.shift_c = shift2;
+        if (fin) { P.out_hi = hout.hi; P.out_lo = hout.lo_off(); P.out_plane = ntot; }
+        else {
+            StatBufs sb;
+            if (!take_stats(sa, F / 32, pl.num_sms, &sb)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
+            P.nstat = F / 32;
+            P.sink.partial = sb.partial; P.sink.total = sb.total; P.sink.counter = sb.counter; P.sink.nsets = F / 32; P.sink.stride = pl.num_sms; P.sink.comm = comm;
+            P.aff.scale = scale2; P.aff.shift = shift2; P.aff.gamma = cp.gn2_w; P.aff.beta = cp.gn2_b; P.aff.channels = F; P.aff.ch_per_set = 32; P.aff.eps = cd.eps;
+        }
+        URNN_TRY(plan_chain(op.c, pl.num_sms));
         ops.push_back(op);
     }
     return URNN_OK;
@@ -449,6 +539,7 @@ int build_plan(Plan& pl, const urnn_ed_desc* d, const urnn_ed_params* p, void* w
             for (; tagged < ops.size(); ++tagged) {
                 Op& o = ops[tagged];
                 if (o.kind == 1) snprintf(o.name, sizeof(o.name), "%s.blend", what);
+                else if (o.kind == 2) snprintf(o.name, sizeof(o.name), o.c.P.final ? "%s.C'" : "%s.B'", what);
                 else if (o.g.P.gate_ch) snprintf(o.name, sizeof(o.name), "%s.B", what);
                 else if (o.g.P.epi == EPI_STATS_F32) snprintf(o.name, sizeof(o.name), gi++ ? "%s.A%d" : "%s.A", what, gi);
                 else snprintf(o.name, sizeof(o.name), gi++ ? "%s.%d" : "%s", what, gi);
@@ -469,10 +560,10 @@ int build_plan(Plan& pl, const urnn_ed_desc* d, const urnn_ed_params* p, void* w
         URNN_TRY(build_final_stem(pl, ops, out[5], p->dec_stem_w[2], p->dec_stem_b[2], d->dec_conv[2], fp)); tag("stem_out");
         if (q == 1) {                              // weight images are shared: copy the addresses recorded for parity 0
             size_t gi = 0;
-            for (size_t i = 0; i < ops.size(); ++i) if (ops[i].kind == 0) { while (pl.ops[0][gi].kind != 0) ++gi; ops[i].g.P.wimg = pl.ops[0][gi].g.P.wimg; ++gi; }
+            for (size_t i = 0; i < ops.size(); ++i) if (ops[i].kind != 1) { while (pl.ops[0][gi].kind == 1) ++gi; op_wimg(ops[i]) = op_wimg(pl.ops[0][gi]); ++gi; }
         }
     }
-    for (const Op& op : pl.ops[0]) if (op.kind == 0 && op.g.P.wimg == nullptr) { set_error("ed(f16x3): weight image arena too small"); return URNN_E_WORKSPACE; }
+    for (Op& op : pl.ops[0]) if (op.kind != 1 && op_wimg(op) == nullptr) { set_error("ed(f16x3): weight image arena too small"); return URNN_E_WORKSPACE; }
     return URNN_OK;
 }
 
@@ -547,6 +638,7 @@ int step(Plan& pl, int parity, const float* x, int cin, const float* w, long lon
     for (const Op& op : pl.ops[parity]) {
         V2_EV();
         if (op.kind == 0) URNN_TRY(launch_gemm(op.g, st, ev == nullptr));
+        else if (op.kind == 2) URNN_TRY(launch_chain(op.c, st, ev == nullptr));
         else {
             const long long total = (op.b.ntot >> 3) * op.b.F;
             void* args[1] = {(void*)&op.b};

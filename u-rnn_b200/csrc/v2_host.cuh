@@ -4,7 +4,7 @@
 #include <cuda_runtime.h>
 #include <string.h>
 #include <stdlib.h>
-#include "gemm_v2.cuh"
+#include "gemm_v2_chain.cuh"
 
 namespace urnn {
 namespace v2 {
@@ -86,8 +86,13 @@ static inline int plan_gemm(GemmLaunch& L, int num_sms) {
     const int ncols_total = P.acc_mode == ACC_DECONV ? P.nacc * P.N : P.N;
     // accumulators: stride between accumulators of one stage, stages
     if (P.nacc == 1) {
-        int cols = 32; while (cols < 2 * P.N) cols <<= 1;
-        P.tmem_cols = cols; P.acc_stride = cols / 2; P.acc_stages = 2;
+        // up to four accumulator stages: the chain MMA issue -> commit -> epilogue wake-up -> epilogue is latency-bound per
+        // stage (~4 us for a 128-column tile), so the stages in flight set the tile rate
+        int stride = 32; while (stride < P.N) stride <<= 1;
+        int stages = 512 / stride; if (stages > MAX_ACC_STAGES) stages = MAX_ACC_STAGES;
+        if (const char* e = getenv("URNN_V2_STAGES")) { const int cap = atoi(e); if (cap >= 1 && cap < stages) stages = cap; }
+        int cols = 32; while (cols < stages * stride) cols <<= 1;
+        P.tmem_cols = cols; P.acc_stride = stride; P.acc_stages = stages;
     } else {
         int stride = 32; while (stride < P.N) stride <<= 1;
         const int need = P.nacc * stride;
@@ -113,7 +118,20 @@ static inline int plan_gemm(GemmLaunch& L, int num_sms) {
     P.nslots = best;
     P.l2_ahead = 0;
     { const char* e = getenv("URNN_V2_L2HINT"); const int v = e ? atoi(e) : 0; P.l2_hint = v == 1 ? L2_EVICT_FIRST : (v == 2 ? L2_EVICT_LAST : L2_EVICT_NORMAL); }
-    L.smem = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total).total;
+    const SmemPlan sp = smem_plan(P.nkb, P.nrows, P.nslots, P.gate_ch, P.gdepth, ncols_total);
+    L.smem = sp.total;
+    for (int s = 0; s < P.nsteps; ++s) {
+        const Step& st = P.steps[s];
+        MmaStep& m = P.msteps[s];
+        const int kg = st.kglob, kg1 = kg + 16;        // the second K = 16 group may start the next 64-channel weight block
+        m.a_desc = smem_desc_mn_sw128(sp.ring_off, (uint32_t)st.unit_ch * 256u);
+        m.a_lo_delta = ((uint32_t)st.unit_ch * 128u) >> 4;
+        m.b_desc[0] = smem_desc_sw128(sp.w_off + (uint32_t)(kg >> 6) * P.nrows * 128u + (uint32_t)((kg & 63) >> 4) * 32u);
+        m.b_desc[1] = smem_desc_sw128(sp.w_off + (uint32_t)(kg1 >> 6) * P.nrows * 128u + (uint32_t)((kg1 & 63) >> 4) * 32u);
+        m.first = ((P.acc_mode == ACC_POOL ? kg : s) == 0) ? 0u : 1u;
+        m.d_off = P.acc_mode != ACC_DECONV ? (unsigned)(st.acc * P.acc_stride) : 0u;
+        m.nj = (unsigned)(st.unit_ch >> 4);
+    }
     const long long ntiles = P.ntot / TILE_M;
     L.grid = (int)(ntiles < num_sms ? ntiles : num_sms);
     L.gated = P.gate_ch > 0;
@@ -136,6 +154,58 @@ static inline int launch_gemm(const GemmLaunch& L, cudaStream_t st, bool pdl = t
         URNN_CUDA(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
         URNN_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<false>, L.maps[0], L.maps[1], L.maps[2], L.P));
     }
+    URNN_LAUNCH_CHECK();
+    return URNN_OK;
+}
+
+// ---- recompute ("chain") launches of a ConvGRU cell (gemm_v2_chain.cuh)
+struct ChainLaunch { CUtensorMap maps[3]; ChainParams P; int grid; size_t smem; };
+
+static inline int add_chain_steps(ChainLaunch& L, int map, int nch, int k0, int ncols) {
+    const int unit = (nch % 32 == 0) ? 32 : 16;
+    for (int c = 0; c < nch; c += unit) {
+        if (L.P.nsteps >= MAX_STEPS) return -1;
+        L.P.step_ncols[L.P.nsteps] = ncols;
+        Step& s = L.P.steps[L.P.nsteps++];
+        s.map = map; s.c0 = c; s.unit_ch = unit; s.kglob = k0 + c; s.acc = 0; s.pad = 0; s.pix_off = 0;
+    }
+    return k0 + nch;
+}
+
+// true when the cell's [W1 ; W2] image, the gate buffers and a ring of >= min_slots fit in one CTA's shared memory
+static inline int chain_slots(int nkb, int nrows, int F, int gdepth) {
+    for (int ns = 8; ns >= 2; --ns) if (chain_smem(nkb, nrows, ns, F, gdepth).total <= SMEM_MAX) return ns;
+    return 0;
+}
+
+static inline int plan_chain(ChainLaunch& L, int num_sms) {
+    ChainParams& P = L.P;
+    if (P.N % 16 || P.N > 256 || P.F % 32) { set_error("chain: %d accumulator columns / %d gated channels not supported", P.N, P.F); return URNN_E_UNSUPPORTED; }
+    int cols = 32; while (cols < 2 * P.N) cols <<= 1;
+    if (cols > 512) { set_error("chain: two stages of %d columns exceed tensor memory", P.N); return URNN_E_UNSUPPORTED; }
+    P.tmem_cols = cols; P.acc_stride = P.N <= cols / 2 ? cols / 2 : P.N;
+    int gd = 2, ns = chain_slots(P.nkb, P.nrows, P.F, 2);
+    if (ns < 3) { gd = 1; ns = chain_slots(P.nkb, P.nrows, P.F, 1); }
+    if (const char* e = getenv("URNN_V2_CHAIN_GD")) { const int v = atoi(e); if (v == 1 || v == 2) { gd = v; ns = chain_slots(P.nkb, P.nrows, P.F, gd); } }
+    if (ns < 2) { set_error("chain: weights %dx%d (hi+lo) leave no room for the operand ring", P.nrows, P.nkb * 64); return URNN_E_UNSUPPORTED; }
+    if (const char* e = getenv("URNN_V2_SLOTS")) { const int cap = atoi(e); if (cap >= 2 && cap < ns) ns = cap; }
+    P.gdepth = gd; P.nslots = ns;
+    L.smem = chain_smem(P.nkb, P.nrows, P.nslots, P.F, P.gdepth).total;
+    const long long ntiles = P.ntot / TILE_M;
+    L.grid = (int)(ntiles < num_sms ? ntiles : num_sms);
+    return URNN_OK;
+}
+
+static inline int launch_chain(const ChainLaunch& L, cudaStream_t st, bool pdl = true) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(NTHREADS_CHAIN);
+    cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    URNN_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
+    URNN_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, L.maps[0], L.maps[1], L.maps[2], L.P));
     URNN_LAUNCH_CHECK();
     return URNN_OK;
 }
