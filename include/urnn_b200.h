@@ -203,6 +203,21 @@ int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t
                          const float* inputs_dev, float* out_dev, float* prob_dev, float* const* states,
                          void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Device-side post-processing of an inference run.
+ * Replaces, for predictions that are still in HBM, the reference's host path test.py:468 (r_MinMaxScaler,
+ * Dynamic2DFlood.py:379-385, min = 0) + test.py:607-675 compute_metrics: R2, MSE, RMSE, MAE (metres), PeakR2, CSI as streaming
+ * reductions over chunks of time steps.  pred_norm_dev: (nsteps, H, W) normalised model output (what urnn_ed_sequence_dev
+ * writes); gt_mm_dev: (nsteps, H, W) ground truth in mm; both fp32 device buffers.  Per-element arithmetic is fp32 exactly as
+ * numpy's on float32 arrays, sums are fp64, the wet / dry counts are integers (bit-exact).  Call reset once, accumulate for
+ * consecutive chunks (t0 = index of the chunk's first step in the event of T steps), finalize once.
+ * out12_dev (device, 12 doubles): R2, MSE, RMSE, MAE, PeakR2, CSI, tp, fp, fn, t_peak, elements, 0.  Stream-ordered. */
+size_t urnn_metrics_workspace_bytes(int32_t H, int32_t W, int32_t T);
+int urnn_metrics_reset(int32_t H, int32_t W, int32_t T, void* ws, size_t ws_bytes, void* stream);
+int urnn_metrics_accumulate(int32_t H, int32_t W, int32_t T, int32_t t0, int32_t nsteps, const float* pred_norm_dev,
+                            const float* gt_mm_dev, float flood_max, void* ws, size_t ws_bytes, void* stream);
+int urnn_metrics_finalize(int32_t H, int32_t W, int32_t T, float flood_thres, void* ws, size_t ws_bytes, double* out12_dev,
+                          void* stream);
+
 /* Host-only helper (no GPU work): position of pixel (y, x) of the level-`level` map (0: H x W, 1: H/2 x W/2, 2: H/4 x W/4)
  * inside a channel plane of the library's internal phase-separated layout (URNN_MATH_F16X3), and the
  * padded plane size in *plane_elems.  Returns -1 for an invalid request.  Used by the tests to pin the layout. */

@@ -7,8 +7,9 @@ sys.path gets [<this repo>/u-rnn_b200, <reference code dir>] in that order, so
 `src.lib.model.networks.{ConvRNN,encoder,decoder,model,net_params,utils,head.*}` resolve to the B200 package while
 everything the package does not provide (`src.lib.model.networks.losses`, `src.lib.model.earlystopping`,
 `src.lib.utils.*`, `src.lib.dataset.*`, `config`, `configs/`) falls through to the reference tree (`src` and `src.lib`
-are namespace packages there; our `model` / `networks` packages extend their `__path__`).  URNN_MATH=bf16|fp32 selects
-the arithmetic of the gate contractions (default fp32 = parity mode).
+are namespace packages there; our `model` / `networks` packages extend their `__path__`).  URNN_MATH=f16x3|fp32|bf16 selects
+the arithmetic of the gate contractions: f16x3 (default; tcgen05 with fp16 hi+lo split operands, inside the fp32 tolerance),
+fp32 (FFMA parity mode; required for training: the backward kernels are fp32), bf16 (round-1 single-pass mode, short horizons).
 """
 import os
 import runpy
@@ -27,7 +28,7 @@ def main():
     sys.argv = [script] + sys.argv[2:]
     os.chdir(code_dir)                      # the reference resolves configs/ relative to its code directory
     import urnn_b200
-    urnn_b200.set_default_math(os.environ.get("URNN_MATH", "fp32"))
+    urnn_b200.set_default_math(os.environ.get("URNN_MATH", "f16x3"))
     runpy.run_path(script, run_name="__main__")
 
 

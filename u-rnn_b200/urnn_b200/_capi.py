@@ -97,6 +97,10 @@ SIGNATURES = {
     "urnn_ed_event_host_workspace_bytes": (sz, [C.POINTER(EdDesc), C.POINTER(EventDesc)]),
     "urnn_ed_event_host": (C.c_int, [C.POINTER(EdDesc), C.POINTER(EdParams), C.POINTER(EventDesc), vp, vp, vp, vp, vp, vp,
                                      C.POINTER(fp), vp, sz, vp]),
+    "urnn_metrics_workspace_bytes": (sz, [i32, i32, i32]),
+    "urnn_metrics_reset": (C.c_int, [i32, i32, i32, vp, sz, vp]),
+    "urnn_metrics_accumulate": (C.c_int, [i32, i32, i32, i32, i32, vp, vp, f32, vp, sz, vp]),
+    "urnn_metrics_finalize": (C.c_int, [i32, i32, i32, f32, vp, sz, vp, vp]),
     "urnn_comm_local_init": (C.c_int, [i32, i32, vp]),
     "urnn_comm_connect": (C.c_int, [vp]),
     "urnn_comm_destroy": (C.c_int, []),
