@@ -117,6 +117,33 @@ def test_x3_sequence_call_equals_step_loop():
     assert torch.equal(depth, depth2)
 
 
+def test_x3_pipelined_sequence_is_bit_identical(monkeypatch):
+    """Sequence calls run encoder(t+1) and decoder + head (t) on two streams (URNN_V2_PIPE=0: one stream): same bits for
+    the device, host-buffer and event entry points, including odd / even lengths (state ping-pong, buffer reuse at t+2)."""
+    from urnn_b200.runner import SequenceRunner
+    H, W, hist = 48, 36, 3
+    C = 2 * hist + 3
+    net = build_ed(H, W, C)
+    torch.manual_seed(5)
+    st0 = [torch.rand_like(s)[0] - 0.5 for s in zero_states(H, W)]
+    for T in (1, 2, 7, 8):
+        xs = torch.from_numpy(O.synthetic_event_inputs(H, W, T, hist)).to(DEV)
+        res = {}
+        for pipe in ("1", "0"):
+            monkeypatch.setenv("URNN_V2_PIPE", pipe)
+            run = SequenceRunner(net, H, W, C)
+            depth, prob, fin = run.run_dev(xs, states=[s.clone() for s in st0])
+            host = run.run_host(xs.cpu().pin_memory(), states=[s.clone() for s in st0])
+            torch.cuda.synchronize()
+            res[pipe] = (depth.clone(), prob.clone(), [f.clone() for f in fin], host[0].clone() if isinstance(host, tuple) else host.clone())
+        a, b = res["1"], res["0"]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), T
+        for x, y in zip(a[2], b[2]):
+            assert torch.equal(x, y), T
+        assert torch.equal(a[3], b[3]), T
+        assert torch.equal(a[3].to(DEV), a[0]), T            # host-buffer path == device path
+
+
 def _event_inputs_gpu(H, W, hist, T, t0, t1, rain_scale, rain_max, cumsum_rain_max=250.0, seed=42):
     """Steps [t0, t1) of oracle.synthetic_event_inputs built on the device (the full (T, 63, 500, 500) tensor is 11 GB)."""
     rng = np.random.RandomState(seed)

@@ -405,14 +405,15 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
 #ifndef URNN_NO_TC
     if (d->math == URNN_MATH_F16X3) {
         int rc = URNN_OK;
-        seq = v2_seq_begin(d, p, states, sp.step_ws, sp.step_ws_bytes, st, &rc);
+        seq = v2_seq_begin(d, p, states, sp.step_ws, sp.step_ws_bytes, st, &rc, true);
         if (!seq) return rc;
     }
 #endif
+    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};   // f16x3: completion events of the pipelined steps
     for (int t = 0; t < T; ++t) {
         const int b = t & 1;
         if (t + 1 < T) {                                    // prefetch the next input into the other buffer
-            if (t >= 1) URNN_CUDA(cudaStreamWaitEvent(s_in, ev_step[b ^ 1], 0));   // step t-1 has consumed it
+            if (t >= 1) URNN_CUDA(cudaStreamWaitEvent(s_in, seq ? e_in[b ^ 1] : ev_step[b ^ 1], 0));   // step t-1 has consumed it
             URNN_CUDA(cudaMemcpyAsync(sp.in[b ^ 1], inputs_host + (size_t)(t + 1) * in_elems, in_elems * sizeof(float),
                                       cudaMemcpyHostToDevice, s_in));
             URNN_CUDA(cudaEventRecord(ev_in[b ^ 1], s_in));
@@ -421,10 +422,15 @@ int urnn_ed_sequence_host(const urnn_ed_desc* d, const urnn_ed_params* p, int32_
         if (t >= 2) URNN_CUDA(cudaStreamWaitEvent(st, ev_out[b], 0));             // out[b] has been drained to the host
         const float* sin[6]; float* sout[6];
         for (int k = 0; k < 6; ++k) { sin[k] = sp.st[b][k]; sout[k] = sp.st[b ^ 1][k]; }
-        if (seq) URNN_TRY(v2_seq_step(seq, t, sp.in[b], d->Cin, p->enc_stem_w[0], (long long)d->Cin, p->enc_stem_b[0], sp.out[b], st));
-        else URNN_TRY(urnn_ed_step_fwd(d, p, sp.in[b], sin, sout, sp.out[b], sp.step_ws, sp.step_ws_bytes, stream));
-        URNN_CUDA(cudaEventRecord(ev_step[b], st));
-        URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
+        if (seq) {
+            URNN_TRY(v2_seq_step(seq, t, sp.in[b], d->Cin, p->enc_stem_w[0], (long long)d->Cin, p->enc_stem_b[0], sp.out[b], nullptr, nullptr, st,
+                                 &e_in[b], &e_out[b]));
+            URNN_CUDA(cudaStreamWaitEvent(s_out, e_out[b], 0));
+        } else {
+            URNN_TRY(urnn_ed_step_fwd(d, p, sp.in[b], sin, sout, sp.out[b], sp.step_ws, sp.step_ws_bytes, stream));
+            URNN_CUDA(cudaEventRecord(ev_step[b], st));
+            URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
+        }
         URNN_CUDA(cudaMemcpyAsync(out_host + (size_t)t * N, sp.out[b], N * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         URNN_CUDA(cudaEventRecord(ev_out[b], s_out));
     }
@@ -469,19 +475,21 @@ int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t
 #ifndef URNN_NO_TC
     if (d->math == URNN_MATH_F16X3) {
         int rc = URNN_OK;
-        seq = v2_seq_begin(d, p, states, sp.step_ws, sp.step_ws_bytes, st, &rc);
+        seq = v2_seq_begin(d, p, states, sp.step_ws, sp.step_ws_bytes, st, &rc, true);
         if (!seq) return rc;
     }
 #endif
     for (int t = 0; t < T; ++t) {
         const int b = t & 1;
         const float* x = inputs_dev + (size_t)t * in_elems;
-        if (seq) URNN_TRY(v2_seq_step(seq, t, x, d->Cin, p->enc_stem_w[0], (long long)d->Cin, p->enc_stem_b[0], sp.out[0], st));
-        else {
-            const float* sin[6]; float* sout[6];
-            for (int k = 0; k < 6; ++k) { sin[k] = sp.st[b][k]; sout[k] = sp.st[b ^ 1][k]; }
-            URNN_TRY(urnn_ed_step_fwd(d, p, x, sin, sout, sp.out[0], sp.step_ws, sp.step_ws_bytes, stream));
+        if (seq) {                                          // the two planes of the step's result are copied out on the decoder's stream
+            URNN_TRY(v2_seq_step(seq, t, x, d->Cin, p->enc_stem_w[0], (long long)d->Cin, p->enc_stem_b[0], sp.out[0], out_dev + (size_t)t * N,
+                                 prob_dev ? prob_dev + (size_t)t * N : nullptr, st, nullptr, nullptr));
+            continue;
         }
+        const float* sin[6]; float* sout[6];
+        for (int k = 0; k < 6; ++k) { sin[k] = sp.st[b][k]; sout[k] = sp.st[b ^ 1][k]; }
+        URNN_TRY(urnn_ed_step_fwd(d, p, x, sin, sout, sp.out[0], sp.step_ws, sp.step_ws_bytes, stream));
         URNN_CUDA(cudaMemcpyAsync(out_dev + (size_t)t * N, sp.out[0], N * sizeof(float), cudaMemcpyDeviceToDevice, st));
         if (prob_dev) URNN_CUDA(cudaMemcpyAsync(prob_dev + (size_t)t * N, sp.out[0] + N, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
@@ -607,10 +615,11 @@ int urnn_ed_event_host(const urnn_ed_desc* d, const urnn_ed_params* p, const urn
 #ifndef URNN_NO_TC
     if (d->math == URNN_MATH_F16X3) {
         int rc = URNN_OK;
-        seq = v2_seq_begin(d, p, states, ep.step_ws, ep.step_ws_bytes, st, &rc);
+        seq = v2_seq_begin(d, p, states, ep.step_ws, ep.step_ws_bytes, st, &rc, true);
         if (!seq) return rc;
     }
 #endif
+    cudaEvent_t e_out[2] = {nullptr, nullptr};
     // ---- T steps, states ping-pong between the caller's buffers and the workspace
     for (int t = 0; t < T; ++t) {
         const int b = t & 1;
@@ -618,10 +627,14 @@ int urnn_ed_event_host(const urnn_ed_desc* d, const urnn_ed_params* p, const urn
         const float* sin[6]; float* sout[6];
         for (int k = 0; k < 6; ++k) { sin[k] = b ? ep.st[k] : states[k]; sout[k] = b ? states[k] : ep.st[k]; }
         Stem1 s1{ep.maps, 3, p->enc_stem_w[0] + 2 * ev->hist, (long)d->Cin, ep.bias_all + (size_t)t * cout0};
-        if (seq) URNN_TRY(v2_seq_step(seq, t, s1.x, s1.cin, s1.w, s1.w_ld, s1.b, ep.out[b], st));
-        else URNN_TRY(ed_step_impl(d, p, s1, sin, sout, ep.out[b], ep.step_ws, ep.step_ws_bytes, stream));
-        URNN_CUDA(cudaEventRecord(ev_step[b], st));
-        URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
+        if (seq) {
+            URNN_TRY(v2_seq_step(seq, t, s1.x, s1.cin, s1.w, s1.w_ld, s1.b, ep.out[b], nullptr, nullptr, st, nullptr, &e_out[b]));
+            URNN_CUDA(cudaStreamWaitEvent(s_out, e_out[b], 0));
+        } else {
+            URNN_TRY(ed_step_impl(d, p, s1, sin, sout, ep.out[b], ep.step_ws, ep.step_ws_bytes, stream));
+            URNN_CUDA(cudaEventRecord(ev_step[b], st));
+            URNN_CUDA(cudaStreamWaitEvent(s_out, ev_step[b], 0));
+        }
         URNN_CUDA(cudaMemcpyAsync(out_host + (size_t)t * N, ep.out[b], N * sizeof(float), cudaMemcpyDeviceToHost, s_out));
         URNN_CUDA(cudaEventRecord(ev_out[b], s_out));
     }

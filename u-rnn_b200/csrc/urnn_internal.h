@@ -52,8 +52,13 @@ long long v2_layout_index(int H, int W, int level, int y, int x, long long* ntot
 size_t v2_step_workspace_bytes(const urnn_ed_desc* d);
 int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float* x, int cin, const float* w, long long w_ld, const float* b,
                      const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
-V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc);
-int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st);
+// pipelined: encoder(t+1) and decoder + head (t) on two internal streams (single GPU; URNN_V2_PIPE=0 disables)
+V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc,
+                    bool pipelined = false);
+// one step; work queued on `st` before the call is respected, completion is reported through the two events (not joined
+// into `st`): *in_done = the step's input has been consumed, *out_done = `out` / depth_dst / prob_dst are complete
+int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out,
+                float* depth_dst, float* prob_dst, cudaStream_t st, cudaEvent_t* in_done, cudaEvent_t* out_done);
 int v2_seq_profile(V2Seq* s, int T, const float* inputs, size_t in_elems, int cin, const float* w, long long w_ld, const float* b, float* out,
                    cudaStream_t st, float* op_ms, char* names, int max_ops, int* nops);
 int v2_seq_end(V2Seq* s, int T, float* const* states, cudaStream_t st);

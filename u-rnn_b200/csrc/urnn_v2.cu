@@ -202,6 +202,16 @@ struct Plan {
     SplitMap st[2][6];                         // recurrent states, ping-pong (reference order: e1 e2 e3 d(1/4) d(1/2) d(1x))
     SplitMap s[3], up3, up2;                   // stem outputs, deconv outputs
     float *G, *C, *feat;                       // pre-GN maps (largest cell), decoder features (NCHW fp32)
+    float *G2, *C2;                            // the decoder cells' own pre-GN maps (encoder of step t+1 overlaps decoder of step t)
+    size_t n_enc[2];                           // ops[q][0 .. n_enc[q]) = encoder, the rest = decoder
+    // two-stream software pipeline of a sequence call (single GPU): encoder(t+1) || decoder + head (t)
+    bool pipe = false; cudaStream_t sE = nullptr, sD = nullptr; cudaEvent_t ev_call = nullptr, evE[2] = {nullptr, nullptr}, evD[2] = {nullptr, nullptr};
+    ~Plan() {
+        if (sE) cudaStreamDestroy(sE);
+        if (sD) cudaStreamDestroy(sD);
+        if (ev_call) cudaEventDestroy(ev_call);
+        for (int i = 0; i < 2; ++i) { if (evE[i]) cudaEventDestroy(evE[i]); if (evD[i]) cudaEventDestroy(evD[i]); }
+    }
     void* head_ws; size_t head_ws_bytes;
     char* wimg; size_t wimg_cap, wimg_used;
     WImgBatch wb;
@@ -235,6 +245,7 @@ static int layout_plan(Plan& pl, const urnn_ed_desc* d, void* ws) {
     size_t gmax = 0, cmax = 0;
     for (int k = 0; k < 6; ++k) { const size_t n = (size_t)l.ntot[state_level(k)]; gmax = std::max(gmax, 2 * (size_t)ch[k] * n); cmax = std::max(cmax, (size_t)ch[k] * n); }
     pl.G = a.take<float>(gmax); pl.C = a.take<float>(cmax);
+    pl.G2 = a.take<float>(gmax); pl.C2 = a.take<float>(cmax);
     pl.feat = a.take<float>((size_t)d->dec_conv[2] * d->H * d->W);
     pl.head_ws_bytes = head_fwd_fp32_workspace(d->H, d->W);
     pl.head_ws = a.take<char>(pl.head_ws_bytes);
@@ -277,7 +288,7 @@ static bool chain_fits(int F, int Keff);
 // One (Skip-)ConvGRU cell step (ConvRNN.py:140-190) as sweep A (gates, GN-1 statistics), sweep B (candidate, GN-2
 // statistics) and the blend.  x / e may be absent (decoder stage 3: x = None -> its weight columns are skipped; encoder: no e).
 static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
-                      const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity) {
+                      const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity, float* Gmap, float* Cmap) {
     const int F = cd.F, Cx = cd.Cx;
     const int Ch = cd.variant == URNN_CELL_DECODER ? 2 * F : F;
     const int Ktot = Cx + Ch, kskip = x ? 0 : Cx, Keff = Ktot - kskip;
@@ -305,7 +316,7 @@ static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_
         P.N = N; P.nrows = N; P.nkb = nkb;
         P.wimg = first_parity ? add_wimg(pl, cp.w1 + (long long)n0 * Ktot, Ktot, 1, 0, 1 << 30, N, N, Keff, kskip) : nullptr;
         P.bias = cp.b1 + n0; P.nbias = N;
-        P.epi = EPI_STATS_F32; P.out_f32 = pl.G + (long long)n0 * ntot; P.out_plane = ntot; P.store_c0 = 0; P.store_c1 = N;
+        P.epi = EPI_STATS_F32; P.out_f32 = Gmap + (long long)n0 * ntot; P.out_plane = ntot; P.store_c0 = 0; P.store_c1 = N;
         StatBufs sb;
         if (!take_stats(sa, N / 32, pl.num_sms, &sb)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
         P.nstat = N / 32;
@@ -325,11 +336,11 @@ static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_
         if (e) { segs[m] = e; k = add_segment_steps(op.g, m, e->C, k, 0, 0); ++m; }
         for (int i = 0; i < 3; ++i) { const SplitMap* sm = segs[i] ? segs[i] : &h; URNN_TRY(make_split_tmap(&op.g.maps[i], *sm, sm->C % 32 == 0 ? 32 : 16, 2)); }
         P.gate_ch = F; P.gate_k0 = k; P.gate_h = h.hi; P.gate_h_plane = ntot; P.gate_h_lo = h.lo_off();
-        P.gate_pre = pl.G + (long long)F * ntot; P.gate_pre_plane = ntot; P.gate_scale = scale1 + F; P.gate_shift = shift1 + F;
+        P.gate_pre = Gmap + (long long)F * ntot; P.gate_pre_plane = ntot; P.gate_scale = scale1 + F; P.gate_shift = shift1 + F;
         P.N = F; P.nrows = F; P.nkb = nkb;
         P.wimg = first_parity ? add_wimg(pl, cp.w2, Ktot, 1, 0, 1 << 30, F, F, Keff, kskip) : nullptr;
         P.bias = cp.b2; P.nbias = F;
-        P.epi = EPI_STATS_F32; P.out_f32 = pl.C; P.out_plane = ntot; P.store_c0 = 0; P.store_c1 = F;
+        P.epi = EPI_STATS_F32; P.out_f32 = Cmap; P.out_plane = ntot; P.store_c0 = 0; P.store_c1 = F;
         StatBufs sb;
         if (!take_stats(sa, F / 32, pl.num_sms, &sb) || !take_affine(sa, F, &scale2, &shift2)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
         P.nstat = F / 32;
@@ -341,7 +352,7 @@ static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_
     // ---- blend
     {
         Op op; op.kind = 1; memset(&op.g, 0, sizeof(op.g));
-        op.b = BlendArgs{pl.G, pl.C, h.hi, h.lo_off(), hout.hi, hout.lo_off(), scale1, shift1, scale2, shift2, F, ntot};
+        op.b = BlendArgs{Gmap, Cmap, h.hi, h.lo_off(), hout.hi, hout.lo_off(), scale1, shift1, scale2, shift2, F, ntot};
         ops.push_back(op);
     }
     return URNN_OK;
@@ -546,18 +557,29 @@ int build_plan(Plan& pl, const urnn_ed_desc* d, const urnn_ed_params* p, void* w
             }
         };
         // encoder (encoder.py:187-215)
-        URNN_TRY(build_cell(pl, ops, sq, enc[0], p->enc_cell[0], 0, &pl.s[0], nullptr, in[0], out[0], fp)); tag("enc1");
+        URNN_TRY(build_cell(pl, ops, sq, enc[0], p->enc_cell[0], 0, &pl.s[0], nullptr, in[0], out[0], fp, pl.G, pl.C)); tag("enc1");
         URNN_TRY(build_pool_stem(pl, ops, out[0], 0, pl.s[1], p->enc_stem_w[1], p->enc_stem_b[1], fp)); tag("stem2");
-        URNN_TRY(build_cell(pl, ops, sq, enc[1], p->enc_cell[1], 1, &pl.s[1], nullptr, in[1], out[1], fp)); tag("enc2");
+        URNN_TRY(build_cell(pl, ops, sq, enc[1], p->enc_cell[1], 1, &pl.s[1], nullptr, in[1], out[1], fp, pl.G, pl.C)); tag("enc2");
         URNN_TRY(build_pool_stem(pl, ops, out[1], 1, pl.s[2], p->enc_stem_w[2], p->enc_stem_b[2], fp)); tag("stem3");
-        URNN_TRY(build_cell(pl, ops, sq, enc[2], p->enc_cell[2], 2, &pl.s[2], nullptr, in[2], out[2], fp)); tag("enc3");
+        URNN_TRY(build_cell(pl, ops, sq, enc[2], p->enc_cell[2], 2, &pl.s[2], nullptr, in[2], out[2], fp, pl.G, pl.C)); tag("enc3");
+        pl.n_enc[q] = ops.size();
         // decoder (decoder.py:173-217): deepest first; stage 3 has no x (ConvRNN.py:143-146)
-        URNN_TRY(build_cell(pl, ops, sq, dec[0], p->dec_cell[0], 2, nullptr, &out[2], in[3], out[3], fp)); tag("dec3");
+        URNN_TRY(build_cell(pl, ops, sq, dec[0], p->dec_cell[0], 2, nullptr, &out[2], in[3], out[3], fp, pl.G2, pl.C2)); tag("dec3");
         URNN_TRY(build_deconv(pl, ops, out[3], 2, pl.up3, p->dec_stem_w[0], p->dec_stem_b[0], fp)); tag("deconv3");
-        URNN_TRY(build_cell(pl, ops, sq, dec[1], p->dec_cell[1], 1, &pl.up3, &out[1], in[4], out[4], fp)); tag("dec2");
+        URNN_TRY(build_cell(pl, ops, sq, dec[1], p->dec_cell[1], 1, &pl.up3, &out[1], in[4], out[4], fp, pl.G2, pl.C2)); tag("dec2");
         URNN_TRY(build_deconv(pl, ops, out[4], 1, pl.up2, p->dec_stem_w[1], p->dec_stem_b[1], fp)); tag("deconv2");
-        URNN_TRY(build_cell(pl, ops, sq, dec[2], p->dec_cell[2], 0, &pl.up2, &out[0], in[5], out[5], fp)); tag("dec1");
+        URNN_TRY(build_cell(pl, ops, sq, dec[2], p->dec_cell[2], 0, &pl.up2, &out[0], in[5], out[5], fp, pl.G2, pl.C2)); tag("dec1");
         URNN_TRY(build_final_stem(pl, ops, out[5], p->dec_stem_w[2], p->dec_stem_b[2], d->dec_conv[2], fp)); tag("stem_out");
+        {   // experiment: cap the persistent grids of the encoder / decoder launches (SM partitioning between the two pipeline streams)
+            const char* ce = getenv("URNN_V2_GRID_E"); const char* cd_ = getenv("URNN_V2_GRID_D");
+            const int capE = ce ? atoi(ce) : 0, capD = cd_ ? atoi(cd_) : 0;
+            for (size_t i = 0; i < ops.size(); ++i) {
+                const int cap = i < pl.n_enc[q] ? capE : capD;
+                if (cap <= 0) continue;
+                if (ops[i].kind == 0 && ops[i].g.grid > cap) ops[i].g.grid = cap;
+                if (ops[i].kind == 2 && ops[i].c.grid > cap) ops[i].c.grid = cap;
+            }
+        }
         if (q == 1) {                              // weight images are shared: copy the addresses recorded for parity 0
             size_t gi = 0;
             for (size_t i = 0; i < ops.size(); ++i) if (ops[i].kind != 1) { while (pl.ops[0][gi].kind == 1) ++gi; op_wimg(ops[i]) = op_wimg(pl.ops[0][gi]); ++gi; }
@@ -653,6 +675,90 @@ int step(Plan& pl, int parity, const float* x, int cin, const float* w, long lon
     return URNN_OK;
 }
 
+// ---- two-stream software pipeline of a sequence call
+// The encoder of step t+1 needs the encoder states of step t and the next input, not the decoder of step t; the decoder +
+// head of step t need the encoder outputs of step t and the decoder states of step t-1.  Every GEMM launch is one
+// persistent CTA per SM with a serial tail (CTAs finish up to 25 % apart, then the last CTA folds the statistics) and a
+// prologue (weight image, TMEM): with the two halves on two streams the hardware fills one kernel's tail with the other
+// stream's CTAs.  Buffers: the encoder states ping-pong, so encoder(t+2) overwrites what decoder(t) reads as skip input
+// -> one event wait; the pre-norm scratch maps exist twice (G, C / G2, C2).  Single GPU only: the in-kernel statistic
+// exchange of a sharded run relies on all ranks issuing their exchanges in the same order.
+static int launch_ops(Plan& pl, int parity, size_t i0, size_t i1, cudaStream_t st) {
+    for (size_t i = i0; i < i1; ++i) {
+        const Op& op = pl.ops[parity][i];
+        if (op.kind == 0) URNN_TRY(launch_gemm(op.g, st, true));
+        else if (op.kind == 2) URNN_TRY(launch_chain(op.c, st, true));
+        else {
+            const long long total = (op.b.ntot >> 3) * op.b.F;
+            void* args[1] = {(void*)&op.b};
+            URNN_TRY(launch_ew((const void*)blend_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, args));
+        }
+    }
+    return URNN_OK;
+}
+
+int pipe_enable(Plan& pl, bool want) {
+    URNN_CUDA(cudaEventCreateWithFlags(&pl.ev_call, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        URNN_CUDA(cudaEventCreateWithFlags(&pl.evE[i], cudaEventDisableTiming));
+        URNN_CUDA(cudaEventCreateWithFlags(&pl.evD[i], cudaEventDisableTiming));
+    }
+    CommDev c; current_comm(&c);
+    const char* e = getenv("URNN_V2_PIPE");
+    if (!want || c.world > 1 || (e && atoi(e) == 0)) return URNN_OK;
+    URNN_CUDA(cudaStreamCreateWithFlags(&pl.sE, cudaStreamNonBlocking));
+    URNN_CUDA(cudaStreamCreateWithFlags(&pl.sD, cudaStreamNonBlocking));
+    pl.pipe = true;
+    return URNN_OK;
+}
+
+// One step of a sequence.  Work already queued on `st` is respected (the encoder waits for it); completion is NOT joined
+// back into `st`: *in_done fires when the step's input has been consumed, *out_done when `out` (and the optional copies
+// depth_dst / prob_dst of its two planes) is complete.  Without the pipeline both are recorded on `st`.
+int seq_step(Plan& pl, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out,
+             float* depth_dst, float* prob_dst, cudaStream_t st, cudaEvent_t* in_done, cudaEvent_t* out_done) {
+    const urnn_ed_desc& d = pl.d;
+    const int parity = t & 1;
+    const size_t N = (size_t)d.H * d.W;
+    cudaStream_t sE = pl.pipe ? pl.sE : st, sD = pl.pipe ? pl.sD : st;
+    if (pl.pipe) {
+        URNN_CUDA(cudaEventRecord(pl.ev_call, st));
+        URNN_CUDA(cudaStreamWaitEvent(sE, pl.ev_call, 0));
+        if (t >= 2) URNN_CUDA(cudaStreamWaitEvent(sE, pl.evD[parity], 0));      // decoder(t-2) has read the states encoder(t) overwrites
+    }
+    {
+        Stem1Args a{x, cin, w, w_ld, b, d.enc_conv[0], d.lrelu_slope, d.H, d.W, d.W / 4, pl.lay.phased, pl.lay.n4p, pl.s[0].ntot, pl.s[0].hi, pl.s[0].lo_off()};
+        const long long nthr = (long long)d.H * (d.W / 4);
+        const size_t smem = (size_t)(((d.enc_conv[0] + 15) / 16) * 16) * (cin + 1) * sizeof(float);
+        if (smem > 48 * 1024) { set_error("stage-1 stem: %d x %d weights exceed 48 KB of shared memory", d.enc_conv[0], cin); return URNN_E_UNSUPPORTED; }
+        void* args[1] = {(void*)&a};
+        URNN_TRY(launch_ew((const void*)stem1_kernel, dim3((unsigned)((nthr + 63) / 64)), dim3(64), smem, sE, args));
+    }
+    URNN_TRY(launch_ops(pl, parity, 0, pl.n_enc[parity], sE));
+    if (pl.pipe) {
+        URNN_CUDA(cudaEventRecord(pl.evE[parity], sE));
+        URNN_CUDA(cudaStreamWaitEvent(sD, pl.evE[parity], 0));
+    }
+    URNN_TRY(launch_ops(pl, parity, pl.n_enc[parity], pl.ops[parity].size(), sD));
+    URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, sD));
+    if (depth_dst) URNN_CUDA(cudaMemcpyAsync(depth_dst, out, N * sizeof(float), cudaMemcpyDeviceToDevice, sD));
+    if (prob_dst) URNN_CUDA(cudaMemcpyAsync(prob_dst, out + N, N * sizeof(float), cudaMemcpyDeviceToDevice, sD));
+    URNN_CUDA(cudaEventRecord(pl.evD[parity], sD));
+    if (!pl.pipe) URNN_CUDA(cudaEventRecord(pl.evE[parity], st));
+    if (in_done) *in_done = pl.evE[parity];
+    if (out_done) *out_done = pl.evD[parity];
+    return URNN_OK;
+}
+
+// joins the pipeline back into `st` (everything issued so far is complete for work queued on `st` afterwards)
+int seq_join(Plan& pl, cudaStream_t st) {
+    if (!pl.pipe) return URNN_OK;
+    cudaEvent_t e = pl.ev_call;
+    URNN_CUDA(cudaEventRecord(e, pl.sE)); URNN_CUDA(cudaStreamWaitEvent(st, e, 0));
+    URNN_CUDA(cudaEventRecord(e, pl.sD)); URNN_CUDA(cudaStreamWaitEvent(st, e, 0));
+    return URNN_OK;
+}
+
 // T timed steps: mean milliseconds of every launch (CUDA events on the launching stream), names as "stem1", "enc1.A", ...
 int profile(Plan& pl, int T, const float* inputs, size_t in_elems, int cin, const float* w, long long w_ld, const float* b, float* out,
             cudaStream_t st, float* op_ms, char* names, int max_ops, int* nops) {
@@ -736,16 +842,19 @@ int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float
                      const float* const* sin, float* const* sout, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
     return v2::step_fwd_nchw(d, p, x, cin, w, w_ld, b, sin, sout, out, ws, ws_bytes, st);
 }
-V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc) {
+V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc,
+                    bool pipelined) {
     std::unique_ptr<v2::Plan> pl(new v2::Plan());
     *rc = v2::build_plan(*pl, d, p, ws, ws_bytes);
     if (*rc == URNN_OK) *rc = v2::prepare(*pl, st);
     if (*rc == URNN_OK) *rc = v2::load_states(*pl, 0, states, st);
+    if (*rc == URNN_OK) *rc = v2::pipe_enable(*pl, pipelined);
     if (*rc != URNN_OK) return nullptr;
     return reinterpret_cast<V2Seq*>(pl.release());
 }
-int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out, cudaStream_t st) {
-    return v2::step(*reinterpret_cast<v2::Plan*>(s), t & 1, x, cin, w, w_ld, b, out, st);
+int v2_seq_step(V2Seq* s, int t, const float* x, int cin, const float* w, long long w_ld, const float* b, float* out,
+                float* depth_dst, float* prob_dst, cudaStream_t st, cudaEvent_t* in_done, cudaEvent_t* out_done) {
+    return v2::seq_step(*reinterpret_cast<v2::Plan*>(s), t, x, cin, w, w_ld, b, out, depth_dst, prob_dst, st, in_done, out_done);
 }
 int v2_seq_profile(V2Seq* s, int T, const float* inputs, size_t in_elems, int cin, const float* w, long long w_ld, const float* b, float* out,
                    cudaStream_t st, float* op_ms, char* names, int max_ops, int* nops) {
@@ -753,7 +862,9 @@ int v2_seq_profile(V2Seq* s, int T, const float* inputs, size_t in_elems, int ci
 }
 int v2_seq_end(V2Seq* s, int T, float* const* states, cudaStream_t st) {
     std::unique_ptr<v2::Plan> pl(reinterpret_cast<v2::Plan*>(s));
-    return states ? v2::store_states(*pl, T & 1, states, st) : URNN_OK;
+    if (!states) { if (pl->pipe) { cudaStreamSynchronize(pl->sE); cudaStreamSynchronize(pl->sD); } return URNN_OK; }   // error path: drain before the streams die
+    URNN_TRY(v2::seq_join(*pl, st));
+    return v2::store_states(*pl, T & 1, states, st);
 }
 
 }  // namespace urnn
