@@ -380,7 +380,8 @@ def run_ours(a):
                                   "fp32": "fp32 FFMA: atol 1e-5 / rtol 1e-4 vs the reference",
                                   "bf16": "single-pass bf16 operands: short horizons only (outside the config-3 tolerance at T=180)"}[a.math],
                        "sharding": "row bands, in-kernel NVLink statistic all-reduce" if world > 1 else "none",
-                       "value_path": f"urnn_ed_sequence_dev (C ABI, device buffers), {chunk}-step calls"},
+                       "value_path": f"urnn_ed_sequence_dev (C ABI, device buffers), {chunk}-step calls"
+                                     + ("; encoder(t+1) overlaps decoder+head(t) on two streams" if world == 1 and a.math == "f16x3" and H * W <= (4 << 20) else "")},
             "gpu_launches": int(launches), "clocks": clk.summary()}
     if sharded_parity is not None:
         line["sharded_parity"] = sharded_parity
@@ -446,7 +447,8 @@ def run_ours(a):
         step_alg = (C + 2 * 188 + 160 + 1) * 4 * N
         roofline = {"bound": "hbm", "kernel": f"decoder stage-1 Skip-ConvGRU cell step (sweep A, sweep B, blend) at {H}x{W}, math={a.math}",
                     "achieved": dec1["achieved"], "peak": peak, "unit": "GB/s", "frac": dec1["frac"],
-                    "traffic": traffic["dec1"] if traffic else None, "peak_source": peak_src,
+                    "traffic": traffic["dec1"] if traffic else None, "traffic_note": traffic.get("note") if traffic else None,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dec1["algorithmic_bytes"], "ms_per_launch": dec1["ms_per_launch_group"],
                     "worst_cell": dict(enc1, kernel="encoder stage-1 ConvGRU cell step", traffic=traffic["enc1"] if traffic else None),
                     "per_launch_us": {k: round(v * 1e3, 1) for k, v in tab},

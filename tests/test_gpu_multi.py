@@ -54,7 +54,16 @@ def _worker(rank, world, port, tmp, H, T):
         for i, c in enumerate(sc):
             e = max(e, float(np.abs(st[i].cpu().numpy()[0] - ref[f"state{i}"][:, r0 // c:(r0 + rows) // c]).max()))
         errs[math] = e
-    np.save(os.path.join(tmp, f"err{rank}.npy"), np.array([errs[m] for m in MODES]))
+        if math == "f16x3":
+            # the sequence entry point: encoder(t+1) || decoder + head (t) on two streams, each half on its own exchange lane
+            from urnn_b200.runner import SequenceRunner
+            depth, _, fin = SequenceRunner(net, rows, W, 2 * HIST + 3).run_dev(xs[:, :, r0:r0 + rows].contiguous().to(dev), want_prob=False)
+            torch.cuda.synchronize()
+            eseq = float(np.abs(depth.cpu().numpy() - ref["seq_depth"][:, r0:r0 + rows]).max())
+            for i, c in enumerate(sc):
+                eseq = max(eseq, float(np.abs(fin[i].cpu().numpy() - ref[f"seq_state{i}"][:, r0 // c:(r0 + rows) // c]).max()))
+            errs["seq"] = eseq
+    np.save(os.path.join(tmp, f"err{rank}.npy"), np.array([errs[m] for m in MODES] + [errs["seq"]]))
     ud.shutdown_spatial_sharding()
     dist.destroy_process_group()
 
@@ -74,7 +83,13 @@ def test_bands_equal_single_gpu(tmp_path, world, T):
         with torch.no_grad():
             for t in range(T):
                 out, *st = net(xs[t][None, None], *st)
-        np.savez(tmp_path / f"ref_{math}.npz", **{f"state{i}": s.cpu().numpy()[0] for i, s in enumerate(st)})
+        ref = {f"state{i}": s.cpu().numpy()[0] for i, s in enumerate(st)}
+        if math == "f16x3":
+            from urnn_b200.runner import SequenceRunner
+            depth, _, fin = SequenceRunner(net, H, W, 2 * HIST + 3).run_dev(xs, want_prob=False)
+            ref["seq_depth"] = depth.cpu().numpy()
+            ref.update({f"seq_state{i}": s.cpu().numpy() for i, s in enumerate(fin)})
+        np.savez(tmp_path / f"ref_{math}.npz", **ref)
         del net
     port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_worker, args=(world, port, str(tmp_path), H, T), nprocs=world, join=True)
@@ -83,6 +98,7 @@ def test_bands_equal_single_gpu(tmp_path, world, T):
         assert e[0] < 1e-5, e          # fp32: only the summation order of the statistics differs
         assert e[1] < 2e-2, e          # bf16: rounding flips at bf16 boundaries, same bound as the single-GPU tests
         assert e[2] < 2e-5, e          # f16x3: split products + merge order of the statistics
+        assert e[3] < 2e-5, e          # f16x3 sequence call (two streams, two exchange lanes) vs the single-GPU sequence call
 
 
 # ------------------------------------------------------------------------------------------------ sharded backward

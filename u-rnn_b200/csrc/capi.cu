@@ -42,7 +42,21 @@ static const size_t kSlotBytes = (size_t)COMM_RING * COMM_MAX_WORLD * COMM_MAX_S
 static const size_t kFlagBytes = (size_t)COMM_RING * COMM_MAX_WORLD * sizeof(unsigned);
 static const size_t kCommBytes = kSlotBytes + kFlagBytes + 256;
 
-void current_comm(CommDev* out) { *out = g_comm; }
+// Two independent exchange lanes (own slots, flags and counter each) share one IPC allocation: lane 0 carries every
+// exchange of the per-operator / fp32 / backward paths and the encoder half of an f16x3 step, lane 1 the decoder half and the
+// head of an f16x3 step -- the two halves run on different streams, and a lane needs all ranks to issue its exchanges in
+// the same order.
+constexpr int kCommLanes = 2;
+void current_comm(CommDev* out, int lane) {
+    *out = g_comm;
+    if (lane <= 0 || lane >= kCommLanes || g_comm.world <= 1) return;
+    const size_t off = (size_t)lane * kCommBytes;
+    for (int r = 0; r < COMM_MAX_WORLD; ++r) {
+        if (out->slots[r]) out->slots[r] = (unsigned long long*)((char*)out->slots[r] + off);
+        if (out->flags[r]) out->flags[r] = (unsigned*)((char*)out->flags[r] + off);
+    }
+    out->seq = (unsigned*)((char*)out->seq + off);
+}
 int comm_world() { return g_comm.world; }
 
 }  // namespace urnn
@@ -655,8 +669,8 @@ int urnn_comm_local_init(int32_t world, int32_t rank, void* handle_out) {
     URNN_CHECK_ARG(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world && handle_out, "comm_local_init: bad argument");
     URNN_CHECK_ARG(sizeof(cudaIpcMemHandle_t) <= URNN_COMM_HANDLE_BYTES, "comm_local_init: IPC handle larger than 64 bytes");
     if (g_comm_local) urnn_comm_destroy();
-    URNN_CUDA(cudaMalloc(&g_comm_local, kCommBytes));
-    URNN_CUDA(cudaMemset(g_comm_local, 0, kCommBytes));
+    URNN_CUDA(cudaMalloc(&g_comm_local, kCommLanes * kCommBytes));
+    URNN_CUDA(cudaMemset(g_comm_local, 0, kCommLanes * kCommBytes));
     URNN_CUDA(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     URNN_CUDA(cudaIpcGetMemHandle(&h, g_comm_local));

@@ -187,7 +187,7 @@ static size_t head_ws_layout(int H, int W, void* ws, size_t ws_bytes, HeadWs* ou
 size_t head_fwd_fp32_workspace(int H, int W) { return head_ws_layout(H, W, nullptr, 0, nullptr); }
 
 int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
-                  const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int comm_lane) {
     HeadWs w;
     size_t need = head_ws_layout(H, W, ws, ws_bytes, &w);
     if (need > ws_bytes) { set_error("head_fwd: workspace %zu < %zu bytes", ws_bytes, need); return URNN_E_WORKSPACE; }
@@ -195,7 +195,7 @@ int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, cons
     long N = (long)H * W;
     HeadDev hd;
     hd.p = *p; hd.cls_thred = cls_thred; hd.eps = ln_eps; hd.slope = slope; hd.plane = N;
-    CommDev comm; current_comm(&comm);
+    CommDev comm; current_comm(&comm, comm_lane);
     hd.count = 16.0 * (double)N * (double)(comm.world > 1 ? comm.world : 1);
     hd.sink = StatSink{w.partial, w.total, w.counter, 5, w.gx, comm};
     head_kernel<0><<<w.gx, 128, 0, st>>>(hd, feat, out, (int)N); URNN_LAUNCH_CHECK();

@@ -7,7 +7,7 @@
 namespace urnn {
 
 struct CommDev;
-void current_comm(CommDev* out);      // the active cross-GPU communicator (world = 1 when none)
+void current_comm(CommDev* out, int lane = 0);      // the active cross-GPU communicator (world = 1 when none); lane: capi.cu
 int comm_world();
 
 // per-cell workspace view shared by the fp32 and tcgen05 paths
@@ -74,8 +74,9 @@ int conv1x1_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, int pool, float slop
 int deconv2x2_lrelu_fwd_fp32(int Cin, int Cout, int H, int W, float slope, const float* x, const float* w,
                              const float* b, float* y, cudaStream_t st);
 size_t head_fwd_fp32_workspace(int H, int W);
+// comm_lane: exchange lane of the LayerNorm statistics (current_comm)
 int head_fwd_fp32(int H, int W, float cls_thred, float ln_eps, float slope, const urnn_head_params* p,
-                  const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+                  const float* feat, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int comm_lane = 0);
 
 // backward, fp32 (urnn_bwd.cu)
 size_t conv1x1_lrelu_bwd_workspace(int Cin, int Cout, int H, int W, int pool);

@@ -205,6 +205,7 @@ struct Plan {
     float *G2, *C2;                            // the decoder cells' own pre-GN maps (encoder of step t+1 overlaps decoder of step t)
     size_t n_enc[2];                           // ops[q][0 .. n_enc[q]) = encoder, the rest = decoder
     // two-stream software pipeline of a sequence call (single GPU): encoder(t+1) || decoder + head (t)
+    bool want_pipe = false;                    // decided before build_plan (sharded + pipelined launches leave two SMs free)
     bool pipe = false; cudaStream_t sE = nullptr, sD = nullptr; cudaEvent_t ev_call = nullptr, evE[2] = {nullptr, nullptr}, evD[2] = {nullptr, nullptr};
     ~Plan() {
         if (sE) cudaStreamDestroy(sE);
@@ -282,20 +283,20 @@ static void fill_common(GemmParams& P, const Plan& pl, int level) {
 }
 
 static int build_cell_y(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
-                        const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity);
+                        const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity, int lane);
 static bool chain_fits(int F, int Keff);
 
 // One (Skip-)ConvGRU cell step (ConvRNN.py:140-190) as sweep A (gates, GN-1 statistics), sweep B (candidate, GN-2
 // statistics) and the blend.  x / e may be absent (decoder stage 3: x = None -> its weight columns are skipped; encoder: no e).
 static int build_cell(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
-                      const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity, float* Gmap, float* Cmap) {
+                      const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity, float* Gmap, float* Cmap, int lane) {
     const int F = cd.F, Cx = cd.Cx;
     const int Ch = cd.variant == URNN_CELL_DECODER ? 2 * F : F;
     const int Ktot = Cx + Ch, kskip = x ? 0 : Cx, Keff = Ktot - kskip;
     const long long ntot = pl.lay.ntot[level];
     if (F % 32 || (x && x->C % 16) || Keff % 16) { set_error("cell(f16x3): channel counts must be multiples of 16 (Cx=%d F=%d)", Cx, F); return URNN_E_UNSUPPORTED; }
-    if (chain_fits(F, Keff)) return build_cell_y(pl, ops, sa, cd, cp, level, x, e, h, hout, first_parity);
-    CommDev comm; current_comm(&comm);
+    if (chain_fits(F, Keff)) return build_cell_y(pl, ops, sa, cd, cp, level, x, e, h, hout, first_parity, lane);
+    CommDev comm; current_comm(&comm, lane);
     // ---- sweep A: G = W1 u + b1 (2F channels), in chunks of output channels whose hi+lo weight image fits beside the ring
     const int nkb = (Keff + 63) / 64;
     int nchunk = 1;
@@ -373,13 +374,13 @@ static bool chain_fits(int F, int Keff) {
 }
 
 static int build_cell_y(Plan& pl, std::vector<Op>& ops, StatAlloc& sa, const urnn_cell_desc& cd, const urnn_cell_params& cp, int level,
-                        const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity) {
+                        const SplitMap* x, const SplitMap* e, const SplitMap& h, const SplitMap& hout, bool first_parity, int lane) {
     const int F = cd.F, Cx = cd.Cx;
     const int Ch = cd.variant == URNN_CELL_DECODER ? 2 * F : F;
     const int Ktot = Cx + Ch, kskip = x ? 0 : Cx, Keff = Ktot - kskip;
     const long long ntot = pl.lay.ntot[level];
     const int nkb = (Keff + 63) / 64;
-    CommDev comm; current_comm(&comm);
+    CommDev comm; current_comm(&comm, lane);
     float *scale1 = nullptr, *shift1 = nullptr, *scale2 = nullptr, *shift2 = nullptr;
     if (!take_affine(sa, 2 * F, &scale1, &shift1) || !take_affine(sa, F, &scale2, &shift2)) { set_error("cell(f16x3): statistics arena too small"); return URNN_E_WORKSPACE; }
     // ---- sweep A: statistics of G = W1 u + b1
@@ -557,22 +558,27 @@ int build_plan(Plan& pl, const urnn_ed_desc* d, const urnn_ed_params* p, void* w
             }
         };
         // encoder (encoder.py:187-215)
-        URNN_TRY(build_cell(pl, ops, sq, enc[0], p->enc_cell[0], 0, &pl.s[0], nullptr, in[0], out[0], fp, pl.G, pl.C)); tag("enc1");
+        URNN_TRY(build_cell(pl, ops, sq, enc[0], p->enc_cell[0], 0, &pl.s[0], nullptr, in[0], out[0], fp, pl.G, pl.C, 0)); tag("enc1");
         URNN_TRY(build_pool_stem(pl, ops, out[0], 0, pl.s[1], p->enc_stem_w[1], p->enc_stem_b[1], fp)); tag("stem2");
-        URNN_TRY(build_cell(pl, ops, sq, enc[1], p->enc_cell[1], 1, &pl.s[1], nullptr, in[1], out[1], fp, pl.G, pl.C)); tag("enc2");
+        URNN_TRY(build_cell(pl, ops, sq, enc[1], p->enc_cell[1], 1, &pl.s[1], nullptr, in[1], out[1], fp, pl.G, pl.C, 0)); tag("enc2");
         URNN_TRY(build_pool_stem(pl, ops, out[1], 1, pl.s[2], p->enc_stem_w[2], p->enc_stem_b[2], fp)); tag("stem3");
-        URNN_TRY(build_cell(pl, ops, sq, enc[2], p->enc_cell[2], 2, &pl.s[2], nullptr, in[2], out[2], fp, pl.G, pl.C)); tag("enc3");
+        URNN_TRY(build_cell(pl, ops, sq, enc[2], p->enc_cell[2], 2, &pl.s[2], nullptr, in[2], out[2], fp, pl.G, pl.C, 0)); tag("enc3");
         pl.n_enc[q] = ops.size();
         // decoder (decoder.py:173-217): deepest first; stage 3 has no x (ConvRNN.py:143-146)
-        URNN_TRY(build_cell(pl, ops, sq, dec[0], p->dec_cell[0], 2, nullptr, &out[2], in[3], out[3], fp, pl.G2, pl.C2)); tag("dec3");
+        URNN_TRY(build_cell(pl, ops, sq, dec[0], p->dec_cell[0], 2, nullptr, &out[2], in[3], out[3], fp, pl.G2, pl.C2, 1)); tag("dec3");
         URNN_TRY(build_deconv(pl, ops, out[3], 2, pl.up3, p->dec_stem_w[0], p->dec_stem_b[0], fp)); tag("deconv3");
-        URNN_TRY(build_cell(pl, ops, sq, dec[1], p->dec_cell[1], 1, &pl.up3, &out[1], in[4], out[4], fp, pl.G2, pl.C2)); tag("dec2");
+        URNN_TRY(build_cell(pl, ops, sq, dec[1], p->dec_cell[1], 1, &pl.up3, &out[1], in[4], out[4], fp, pl.G2, pl.C2, 1)); tag("dec2");
         URNN_TRY(build_deconv(pl, ops, out[4], 1, pl.up2, p->dec_stem_w[1], p->dec_stem_b[1], fp)); tag("deconv2");
-        URNN_TRY(build_cell(pl, ops, sq, dec[2], p->dec_cell[2], 0, &pl.up2, &out[0], in[5], out[5], fp, pl.G2, pl.C2)); tag("dec1");
+        URNN_TRY(build_cell(pl, ops, sq, dec[2], p->dec_cell[2], 0, &pl.up2, &out[0], in[5], out[5], fp, pl.G2, pl.C2, 1)); tag("dec1");
         URNN_TRY(build_final_stem(pl, ops, out[5], p->dec_stem_w[2], p->dec_stem_b[2], d->dec_conv[2], fp)); tag("stem_out");
-        {   // experiment: cap the persistent grids of the encoder / decoder launches (SM partitioning between the two pipeline streams)
+        {   // caps of the persistent grids of the encoder / decoder launches
+            // Sharded + pipelined: the last CTA of a statistics launch spins for its peers and keeps its SM; the other
+            // stream's persistent launch must not need that SM (a 148-CTA grid would run a second wave for one CTA:
+            // 2 GPUs, 500^2 bands: 1.035 ms/step with full grids, 0.955 with 147 CTAs, 0.938 with 146).
+            CommDev cm; current_comm(&cm);
+            const int spare = (pl.want_pipe && cm.world > 1) ? pl.num_sms - 2 : 0;
             const char* ce = getenv("URNN_V2_GRID_E"); const char* cd_ = getenv("URNN_V2_GRID_D");
-            const int capE = ce ? atoi(ce) : 0, capD = cd_ ? atoi(cd_) : 0;
+            const int capE = ce ? atoi(ce) : spare, capD = cd_ ? atoi(cd_) : spare;
             for (size_t i = 0; i < ops.size(); ++i) {
                 const int cap = i < pl.n_enc[q] ? capE : capD;
                 if (cap <= 0) continue;
@@ -669,7 +675,7 @@ int step(Plan& pl, int parity, const float* x, int cin, const float* w, long lon
         V2_EV();
     }
     V2_EV();
-    URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, st));
+    URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, st, 1));
     V2_EV();
 #undef V2_EV
     return URNN_OK;
@@ -681,8 +687,8 @@ int step(Plan& pl, int parity, const float* x, int cin, const float* w, long lon
 // persistent CTA per SM with a serial tail (CTAs finish up to 25 % apart, then the last CTA folds the statistics) and a
 // prologue (weight image, TMEM): with the two halves on two streams the hardware fills one kernel's tail with the other
 // stream's CTAs.  Buffers: the encoder states ping-pong, so encoder(t+2) overwrites what decoder(t) reads as skip input
-// -> one event wait; the pre-norm scratch maps exist twice (G, C / G2, C2).  Single GPU only: the in-kernel statistic
-// exchange of a sharded run relies on all ranks issuing their exchanges in the same order.
+// -> one event wait; the pre-norm scratch maps exist twice (G, C / G2, C2).  Sharded runs: the in-kernel statistic exchange
+// needs every rank to issue its exchanges in the same order, so the two halves use two exchange lanes (current_comm).
 static int launch_ops(Plan& pl, int parity, size_t i0, size_t i1, cudaStream_t st) {
     for (size_t i = i0; i < i1; ++i) {
         const Op& op = pl.ops[parity][i];
@@ -697,15 +703,31 @@ static int launch_ops(Plan& pl, int parity, size_t i0, size_t i1, cudaStream_t s
     return URNN_OK;
 }
 
+// Two streams pay off while the serial head and tail of a launch matter (tens of microseconds against kernels of
+// 20-80 us); on grids of several million cells per GPU the kernels run for milliseconds and the overlap buys nothing.
+// SINGLE GPU ONLY.  In a sharded run the last CTA of every statistics launch spins for its peers; with two streams and
+// programmatic dependent launch, the next launch of the same stream is already resident (blocked in griddepcontrol.wait)
+// and holds the SMs the OTHER stream's launch needs on the peer the spinning CTA is waiting for -> circular wait.
+// Observed: 2 GPUs ran (0.938 ms/step with two SMs left free, against 1.075 on one stream), 4 GPUs deadlocked.  The exchange
+// lanes (current_comm) keep the protocol itself legal; what is missing is a launch order that cannot starve a peer.
+// URNN_V2_PIPE=0 switches the pipeline off, URNN_V2_PIPE=2 forces it in sharded runs (experiments only, can hang).
+bool pipe_wanted(const urnn_ed_desc* d) {
+    CommDev c; current_comm(&c);
+    const char* e = getenv("URNN_V2_PIPE");
+    const int mode = e ? atoi(e) : 1;
+    if (mode == 0) return false;
+    if (c.world > 1) return mode == 2;
+    if (e) return true;
+    return (long long)d->H * d->W <= (4LL << 20);
+}
+
 int pipe_enable(Plan& pl, bool want) {
     URNN_CUDA(cudaEventCreateWithFlags(&pl.ev_call, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         URNN_CUDA(cudaEventCreateWithFlags(&pl.evE[i], cudaEventDisableTiming));
         URNN_CUDA(cudaEventCreateWithFlags(&pl.evD[i], cudaEventDisableTiming));
     }
-    CommDev c; current_comm(&c);
-    const char* e = getenv("URNN_V2_PIPE");
-    if (!want || c.world > 1 || (e && atoi(e) == 0)) return URNN_OK;
+    if (!want) return URNN_OK;
     URNN_CUDA(cudaStreamCreateWithFlags(&pl.sE, cudaStreamNonBlocking));
     URNN_CUDA(cudaStreamCreateWithFlags(&pl.sD, cudaStreamNonBlocking));
     pl.pipe = true;
@@ -740,7 +762,7 @@ int seq_step(Plan& pl, int t, const float* x, int cin, const float* w, long long
         URNN_CUDA(cudaStreamWaitEvent(sD, pl.evE[parity], 0));
     }
     URNN_TRY(launch_ops(pl, parity, pl.n_enc[parity], pl.ops[parity].size(), sD));
-    URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, sD));
+    URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, sD, 1));
     if (depth_dst) URNN_CUDA(cudaMemcpyAsync(depth_dst, out, N * sizeof(float), cudaMemcpyDeviceToDevice, sD));
     if (prob_dst) URNN_CUDA(cudaMemcpyAsync(prob_dst, out + N, N * sizeof(float), cudaMemcpyDeviceToDevice, sD));
     URNN_CUDA(cudaEventRecord(pl.evD[parity], sD));
@@ -845,10 +867,11 @@ int v2_step_fwd_nchw(const urnn_ed_desc* d, const urnn_ed_params* p, const float
 V2Seq* v2_seq_begin(const urnn_ed_desc* d, const urnn_ed_params* p, const float* const* states, void* ws, size_t ws_bytes, cudaStream_t st, int* rc,
                     bool pipelined) {
     std::unique_ptr<v2::Plan> pl(new v2::Plan());
+    pl->want_pipe = pipelined && v2::pipe_wanted(d);
     *rc = v2::build_plan(*pl, d, p, ws, ws_bytes);
     if (*rc == URNN_OK) *rc = v2::prepare(*pl, st);
     if (*rc == URNN_OK) *rc = v2::load_states(*pl, 0, states, st);
-    if (*rc == URNN_OK) *rc = v2::pipe_enable(*pl, pipelined);
+    if (*rc == URNN_OK) *rc = v2::pipe_enable(*pl, pl->want_pipe);
     if (*rc != URNN_OK) return nullptr;
     return reinterpret_cast<V2Seq*>(pl.release());
 }
