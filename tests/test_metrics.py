@@ -95,3 +95,22 @@ def test_cuda_metrics_argument_errors():
         m.result()                                      # only 2 of 4 steps seen
     with pytest.raises(ValueError):
         m.update(torch.zeros(3, 8, 8, device="cuda:0"), torch.zeros(3, 8, 8, device="cuda:0"))
+
+
+def test_metrics_abi_argument_checks_without_a_gpu():
+    """The C entry points validate before touching the device: sizes, NULL workspace, step ranges (no GPU needed)."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "u-rnn_b200"))
+    from urnn_b200 import _capi
+    lib = _capi.load()
+    assert lib.urnn_metrics_workspace_bytes(0, 8, 4) == 0 and lib.urnn_metrics_workspace_bytes(8, 8, 0) == 0
+    need = lib.urnn_metrics_workspace_bytes(500, 500, 180)
+    assert need >= 2 * 500 * 500 * 4 + 180 * 32 and need % 256 == 0          # two fp32 maxima maps + per-step sums
+    assert lib.urnn_metrics_reset(8, 8, 4, None, 0, None) != 0
+    assert b"workspace" in lib.urnn_last_error()
+    fake = C.c_void_p(0x1000)                                                  # never dereferenced: the size check comes first
+    assert lib.urnn_metrics_reset(8, 8, 4, fake, 16, None) != 0
+    assert lib.urnn_metrics_accumulate(8, 8, 4, 3, 2, fake, fake, 5000.0, fake, 1 << 20, None) != 0      # steps [3, 5) of 4
+    assert b"outside" in lib.urnn_last_error()
+    assert lib.urnn_metrics_finalize(8, 8, 4, 150.0, fake, 1 << 20, None, None) != 0
