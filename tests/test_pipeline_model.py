@@ -37,3 +37,31 @@ def test_odd_staging_depth_breaks_the_protocol():
         except AssertionError:
             bad += 1
     assert bad > 0
+
+
+def _load_sharded():
+    spec = importlib.util.spec_from_file_location("sim_sharded_pipeline", os.path.join(ROOT, "tools", "sim_sharded_pipeline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    mod.__name__ = "sim_sharded_pipeline"
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_step_on_one_stream_never_deadlocks(world):
+    """What ships: sharded sequence calls keep every launch on one stream (urnn_v2.cu: pipe_wanted)."""
+    sim = _load_sharded()
+    for seed in range(60):
+        assert sim.run(world=world, streams=1, pdl=True, seed=seed) == "ok", seed
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_two_streams_deadlock_only_with_dependent_launch_residency(world):
+    """The encoder / decoder pipeline in a sharded run: a launch that is already resident under programmatic dependent
+    launch holds the SMs the other stream needs on the peer a spinning last CTA waits for (the 4-GPU hang).
+    Without that residency the two streams always finish -- the order a future sharded pipeline has to use."""
+    sim = _load_sharded()
+    with_pdl = [sim.run(world=world, streams=2, pdl=True, seed=s) for s in range(60)]
+    without = [sim.run(world=world, streams=2, pdl=False, seed=s) for s in range(60)]
+    assert "deadlock" in with_pdl
+    assert set(without) == {"ok"}
