@@ -206,6 +206,7 @@ struct Plan {
     size_t n_enc[2];                           // ops[q][0 .. n_enc[q]) = encoder, the rest = decoder
     // two-stream software pipeline of a sequence call (single GPU): encoder(t+1) || decoder + head (t)
     bool want_pipe = false;                    // decided before build_plan (sharded + pipelined launches leave two SMs free)
+    bool sharded = false;                      // a communicator with world > 1 was active when the plan was built
     bool pipe = false; cudaStream_t sE = nullptr, sD = nullptr; cudaEvent_t ev_call = nullptr, evE[2] = {nullptr, nullptr}, evD[2] = {nullptr, nullptr};
     ~Plan() {
         if (sE) cudaStreamDestroy(sE);
@@ -576,6 +577,7 @@ int build_plan(Plan& pl, const urnn_ed_desc* d, const urnn_ed_params* p, void* w
             // stream's persistent launch must not need that SM (a 148-CTA grid would run a second wave for one CTA:
             // 2 GPUs, 500^2 bands: 1.035 ms/step with full grids, 0.955 with 147 CTAs, 0.938 with 146).
             CommDev cm; current_comm(&cm);
+            pl.sharded = cm.world > 1;
             const int spare = (pl.want_pipe && cm.world > 1) ? pl.num_sms - 2 : 0;
             const char* ce = getenv("URNN_V2_GRID_E"); const char* cd_ = getenv("URNN_V2_GRID_D");
             const int capE = ce ? atoi(ce) : spare, capD = cd_ ? atoi(cd_) : spare;
@@ -634,13 +636,13 @@ int store_states(Plan& pl, int parity, float* const* s_nchw, cudaStream_t st) {
     return URNN_OK;
 }
 
-static int launch_ew(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+static int launch_ew(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args, bool pdl = true) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
     URNN_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
     URNN_LAUNCH_CHECK();
     return URNN_OK;
@@ -689,15 +691,15 @@ int step(Plan& pl, int parity, const float* x, int cin, const float* w, long lon
 // stream's CTAs.  Buffers: the encoder states ping-pong, so encoder(t+2) overwrites what decoder(t) reads as skip input
 // -> one event wait; the pre-norm scratch maps exist twice (G, C / G2, C2).  Sharded runs: the in-kernel statistic exchange
 // needs every rank to issue its exchanges in the same order, so the two halves use two exchange lanes (current_comm).
-static int launch_ops(Plan& pl, int parity, size_t i0, size_t i1, cudaStream_t st) {
+static int launch_ops(Plan& pl, int parity, size_t i0, size_t i1, cudaStream_t st, bool pdl) {
     for (size_t i = i0; i < i1; ++i) {
         const Op& op = pl.ops[parity][i];
-        if (op.kind == 0) URNN_TRY(launch_gemm(op.g, st, true));
-        else if (op.kind == 2) URNN_TRY(launch_chain(op.c, st, true));
+        if (op.kind == 0) URNN_TRY(launch_gemm(op.g, st, pdl));
+        else if (op.kind == 2) URNN_TRY(launch_chain(op.c, st, pdl));
         else {
             const long long total = (op.b.ntot >> 3) * op.b.F;
             void* args[1] = {(void*)&op.b};
-            URNN_TRY(launch_ew((const void*)blend_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, args));
+            URNN_TRY(launch_ew((const void*)blend_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, args, pdl));
         }
     }
     return URNN_OK;
@@ -710,7 +712,9 @@ static int launch_ops(Plan& pl, int parity, size_t i0, size_t i1, cudaStream_t s
 // and holds the SMs the OTHER stream's launch needs on the peer the spinning CTA is waiting for -> circular wait.
 // Observed: 2 GPUs ran (0.938 ms/step with two SMs left free, against 1.075 on one stream), 4 GPUs deadlocked.  The exchange
 // lanes (current_comm) keep the protocol itself legal; what is missing is a launch order that cannot starve a peer.
-// URNN_V2_PIPE=0 switches the pipeline off, URNN_V2_PIPE=2 forces it in sharded runs (experiments only, can hang).
+// URNN_V2_PIPE=0 switches the pipeline off; URNN_V2_PIPE=2 forces it in sharded runs, then without programmatic dependent
+// launch and with two SMs left free (the order the model in tools/sim_sharded_pipeline.py finds safe; NOT yet run on
+// hardware -- the round's GPU time ended with the hang).
 bool pipe_wanted(const urnn_ed_desc* d) {
     CommDev c; current_comm(&c);
     const char* e = getenv("URNN_V2_PIPE");
@@ -743,6 +747,9 @@ int seq_step(Plan& pl, int t, const float* x, int cin, const float* w, long long
     const int parity = t & 1;
     const size_t N = (size_t)d.H * d.W;
     cudaStream_t sE = pl.pipe ? pl.sE : st, sD = pl.pipe ? pl.sD : st;
+    // forced sharded pipeline (URNN_V2_PIPE=2): no programmatic dependent launch -- a launch that is resident before its
+    // predecessor's exchange completed is what lets two ranks starve each other (tools/sim_sharded_pipeline.py)
+    const bool pdl = !(pl.pipe && pl.sharded);
     if (pl.pipe) {
         URNN_CUDA(cudaEventRecord(pl.ev_call, st));
         URNN_CUDA(cudaStreamWaitEvent(sE, pl.ev_call, 0));
@@ -754,14 +761,14 @@ int seq_step(Plan& pl, int t, const float* x, int cin, const float* w, long long
         const size_t smem = (size_t)(((d.enc_conv[0] + 15) / 16) * 16) * (cin + 1) * sizeof(float);
         if (smem > 48 * 1024) { set_error("stage-1 stem: %d x %d weights exceed 48 KB of shared memory", d.enc_conv[0], cin); return URNN_E_UNSUPPORTED; }
         void* args[1] = {(void*)&a};
-        URNN_TRY(launch_ew((const void*)stem1_kernel, dim3((unsigned)((nthr + 63) / 64)), dim3(64), smem, sE, args));
+        URNN_TRY(launch_ew((const void*)stem1_kernel, dim3((unsigned)((nthr + 63) / 64)), dim3(64), smem, sE, args, pdl));
     }
-    URNN_TRY(launch_ops(pl, parity, 0, pl.n_enc[parity], sE));
+    URNN_TRY(launch_ops(pl, parity, 0, pl.n_enc[parity], sE, pdl));
     if (pl.pipe) {
         URNN_CUDA(cudaEventRecord(pl.evE[parity], sE));
         URNN_CUDA(cudaStreamWaitEvent(sD, pl.evE[parity], 0));
     }
-    URNN_TRY(launch_ops(pl, parity, pl.n_enc[parity], pl.ops[parity].size(), sD));
+    URNN_TRY(launch_ops(pl, parity, pl.n_enc[parity], pl.ops[parity].size(), sD, pdl));
     URNN_TRY(head_fwd_fp32(d.H, d.W, d.cls_thred, d.ln_eps, d.lrelu_slope, &pl.p.head, pl.feat, out, pl.head_ws, pl.head_ws_bytes, sD, 1));
     if (depth_dst) URNN_CUDA(cudaMemcpyAsync(depth_dst, out, N * sizeof(float), cudaMemcpyDeviceToDevice, sD));
     if (prob_dst) URNN_CUDA(cudaMemcpyAsync(prob_dst, out + N, N * sizeof(float), cudaMemcpyDeviceToDevice, sD));
