@@ -197,7 +197,10 @@ int urnn_ed_step_fwd(const urnn_ed_desc* d, const urnn_ed_params* p, const float
  * page-locked.  states[6] are device buffers updated in place across the T steps (ping-pong inside ws). */
 /* test.py:356-367 with DEVICE buffers: T steps, inputs_dev (T, Cin, H, W) and out_dev (T, H, W) resident in HBM, the six
  * states (reference order, fp32 NCHW) updated in place.  Workspace: urnn_ed_sequence_dev_workspace_bytes.  Stream-ordered,
- * no synchronisation.  prob_dev may be NULL; otherwise it receives the (T, H, W) wet probabilities. */
+ * no synchronisation.  prob_dev may be NULL; otherwise it receives the (T, H, W) wet probabilities.
+ * URNN_MATH_F16X3 on one GPU: the encoder of step t+1 and the decoder + head of step t run on two internal streams that
+ * fork from `stream` at entry and join it before the states are written back, so the call keeps its stream-ordered
+ * meaning for the caller (URNN_V2_PIPE=0: everything on `stream`).  The same holds for the two _host entry points. */
 size_t urnn_ed_sequence_dev_workspace_bytes(const urnn_ed_desc* d);
 int urnn_ed_sequence_dev(const urnn_ed_desc* d, const urnn_ed_params* p, int32_t T,
                          const float* inputs_dev, float* out_dev, float* prob_dev, float* const* states,
