@@ -129,7 +129,7 @@ def test_bf16_full_size_short_horizon_tracks_fp32():
     SURVEY.md 8d tolerance: rms(d depth) <= 2e-2 * rms(depth) (+ margin for the run-to-run spread of rounding ties),
     mask flip rate <= 0.5 %.  Measured on B200: 1.6e-2 and 0 flips; the drift over the full T = 180 horizon (random-init,
     non-contractive weights: 7 % at T = 36, 13 % at T = 180, R^2 = 0.973) is recorded in profiles/r1_config3_drift.json
-    (tools/config3_drift.py) and discussed in DESIGN.md section 2."""
+    (tests/tools/config3_drift.py) and discussed in DESIGN.md section 2."""
     from src.lib.model.networks.model import ED
     from src.lib.model.networks.net_params import get_network_params
     H = W = 500

@@ -2,7 +2,7 @@
 fp32 parity path of the same library (which is pinned to the reference's outputs at smaller sizes).  Prints the drift
 statistics SURVEY.md 8d asks for: rms(d depth)/rms(depth), max |d state|, wet/dry mask flip rate, R^2."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "u-rnn_b200")]
 import numpy as np, torch
 from oracle import urnn_oracle as O

@@ -1,7 +1,7 @@
 """Bring-up helper: one cell step in bf16 (tcgen05) mode vs the bf16-quantised oracle; prints error stats."""
 import os, sys
 os.environ["CUDA_MODULE_LOADING"] = "EAGER"
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "u-rnn_b200")]
 import numpy as np, torch, faulthandler
 faulthandler.dump_traceback_later(200, exit=True)
